@@ -1,0 +1,610 @@
+// HBM-bound kernels around the tensor-core tiles: layout changes, BatchNorm (train/eval, fwd/bwd), pooling,
+// bilinear resampling.  All tensors are NHWC fp32 with an explicit pixel stride (ld) so channel slices work in place.
+// Each extern "C" entry cites the reference op it stands in for (paths relative to the reference repo).
+#include "common.cuh"
+#include "../../include/cavp_b200.h"
+
+namespace cavp {
+
+// ------------------------------------------------------------------------------------------------ layout
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int n, int c, int hw,
+                                    int cpad) {
+  const long long total = static_cast<long long>(n) * hw;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long img = i / hw;
+    const long long pix = i - img * hw;
+    const float* s = src + img * c * hw + pix;
+    float* d = dst + i * cpad;
+    for (int ch = 0; ch < cpad; ++ch) d[ch] = ch < c ? s[static_cast<long long>(ch) * hw] : 0.f;
+  }
+}
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, float* __restrict__ dst, int n, int c, int hw,
+                                    int ld) {
+  const long long total = static_cast<long long>(n) * hw;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long img = i / hw;
+    const long long pix = i - img * hw;
+    const float* s = src + i * ld;
+    float* d = dst + img * c * hw + pix;
+    for (int ch = 0; ch < c; ++ch) d[static_cast<long long>(ch) * hw] = s[ch];
+  }
+}
+// dst[b][cidx][r] = src[b][r][cidx] with leading dimensions; 32x32 tiles through shared memory
+__global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols,
+                                 long long src_ld, long long dst_ld, long long src_bs, long long dst_bs) {
+  __shared__ float tile[32][33];
+  const float* s = src + blockIdx.z * src_bs;
+  float* d = dst + blockIdx.z * dst_bs;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int r = r0 + j, cc = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (r < rows && cc < cols) ? s[r * src_ld + cc] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int cc = c0 + j, r = r0 + threadIdx.x;
+    if (cc < cols && r < rows) d[cc * dst_ld + r] = tile[threadIdx.x][j];
+  }
+}
+__global__ void add_inplace_kernel(float* __restrict__ dst, const float* __restrict__ src, long long n4, float alpha) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 a = reinterpret_cast<float4*>(dst)[i];
+    const float4 b = reinterpret_cast<const float4*>(src)[i];
+    a.x += alpha * b.x; a.y += alpha * b.y; a.z += alpha * b.z; a.w += alpha * b.w;
+    reinterpret_cast<float4*>(dst)[i] = a;
+  }
+}
+// rows gathered: dst[i][:] = src[idx[i]][:]   (forward_audio feature shuffle, models/cavp_model.py:171-173)
+__global__ void gather_rows_kernel(const float* __restrict__ src, const long long* __restrict__ idx,
+                                   float* __restrict__ dst, int nrows, int c, int accumulate_scatter) {
+  const int r = blockIdx.x;
+  if (r >= nrows) return;
+  const long long sidx = idx[r];
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    if (accumulate_scatter)
+      atomicAdd(dst + sidx * c + ch, src[static_cast<long long>(r) * c + ch]);
+    else
+      dst[static_cast<long long>(r) * c + ch] = src[sidx * c + ch];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ BatchNorm
+// one warp per channel: reduce the per-(m_tile, quarter) partial sums written by the igemm epilogue (fp64 accumulate)
+__global__ void bn_finalize_kernel(const float* __restrict__ partials, int nparts, int ldstat, int C, double count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
+                                   float eps, float* __restrict__ mean_out, float* __restrict__ invstd_out,
+                                   float* __restrict__ scale_out, float* __restrict__ shift_out,
+                                   double* __restrict__ sums_io, int sums_mode) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= C) return;
+  double s1 = 0.0, s2 = 0.0;
+  if (sums_mode != 2) {
+    for (int i = lane; i < nparts; i += 32) {
+      const float* pp = partials + static_cast<size_t>(i) * 2 * ldstat;
+      s1 += pp[warp];
+      s2 += pp[ldstat + warp];
+    }
+    s1 = warp_sum_d(s1);
+    s2 = warp_sum_d(s2);
+  }
+  if (lane == 0) {
+    if (sums_mode == 1) {  // only export local sums (SyncBatchNorm: all-reduced by the host side, then mode 2)
+      sums_io[warp] = s1;
+      sums_io[C + warp] = s2;
+      return;
+    }
+    if (sums_mode == 2) {
+      s1 = sums_io[warp];
+      s2 = sums_io[C + warp];
+    }
+    const double mean = s1 / count;
+    double var = s2 / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = 1.0f / sqrtf(static_cast<float>(var) + eps);
+    const float g = gamma ? gamma[warp] : 1.f, b = beta ? beta[warp] : 0.f;
+    mean_out[warp] = static_cast<float>(mean);
+    invstd_out[warp] = invstd;
+    scale_out[warp] = g * invstd;
+    shift_out[warp] = b - static_cast<float>(mean) * g * invstd;
+    if (running_mean) {
+      const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+      running_mean[warp] = (1.f - momentum) * running_mean[warp] + momentum * static_cast<float>(mean);
+      running_var[warp] = (1.f - momentum) * running_var[warp] + momentum * static_cast<float>(unbiased);
+    }
+  }
+}
+// eval mode: scale/shift from running statistics
+__global__ void bn_eval_coeffs_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      const float* __restrict__ rm, const float* __restrict__ rv, float eps, int C,
+                                      float* __restrict__ scale, float* __restrict__ shift) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= C) return;
+  const float invstd = 1.0f / sqrtf(rv[ch] + eps);
+  const float g = gamma ? gamma[ch] : 1.f, b = beta ? beta[ch] : 0.f;
+  scale[ch] = g * invstd;
+  shift[ch] = b - rm[ch] * g * invstd;
+}
+
+__global__ void bn_apply_kernel(const float* __restrict__ y, int ldy, const float* __restrict__ scale,
+                                const float* __restrict__ shift, const float* __restrict__ res, int ldr,
+                                float* __restrict__ out, int ldo, long long rows, int C4, int act, float slope) {
+  const long long total = rows * C4;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / C4;
+    const int c4 = static_cast<int>(i - r * C4);
+    const float4 v = *reinterpret_cast<const float4*>(y + r * ldy + c4 * 4);
+    const float4 sc = *reinterpret_cast<const float4*>(scale + c4 * 4);
+    const float4 sh = *reinterpret_cast<const float4*>(shift + c4 * 4);
+    float4 o = make_float4(v.x * sc.x + sh.x, v.y * sc.y + sh.y, v.z * sc.z + sh.z, v.w * sc.w + sh.w);
+    if (res) {
+      const float4 rr = *reinterpret_cast<const float4*>(res + r * ldr + c4 * 4);
+      o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+    }
+    o.x = act_fwd(o.x, act, slope); o.y = act_fwd(o.y, act, slope);
+    o.z = act_fwd(o.z, act, slope); o.w = act_fwd(o.w, act, slope);
+    *reinterpret_cast<float4*>(out + r * ldo + c4 * 4) = o;
+  }
+}
+
+// Column reductions of g = dz * act'(z) and g * xhat over a block of rows.  Also used as "activation backward +
+// bias gradient" (y == nullptr) and as a plain column sum (z == nullptr).  grid = (ceil(C4/64), nblk), block = 256.
+__global__ void colreduce_kernel(const float* __restrict__ dz, int lddz, const float* __restrict__ z, int ldz,
+                                 const float* __restrict__ y, int ldy, const float* __restrict__ mean,
+                                 const float* __restrict__ invstd, long long rows, int C4, int act, float slope,
+                                 float* __restrict__ gout, int ldg, float* __restrict__ partials, int ldp) {
+  __shared__ float4 sh[2][4][64];
+  const int cl = threadIdx.x & 63, rl = threadIdx.x >> 6;
+  const int c4 = blockIdx.x * 64 + cl;
+  const long long rows_per = (rows + gridDim.y - 1) / gridDim.y;
+  const long long rbeg = blockIdx.y * rows_per;
+  const long long rend = rbeg + rows_per < rows ? rbeg + rows_per : rows;
+  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+  if (c4 < C4) {
+    float4 mu = s1, is = s1;
+    if (y) {
+      mu = *reinterpret_cast<const float4*>(mean + c4 * 4);
+      is = *reinterpret_cast<const float4*>(invstd + c4 * 4);
+    }
+    for (long long r = rbeg + rl; r < rend; r += 4) {
+      float4 g = *reinterpret_cast<const float4*>(dz + r * lddz + c4 * 4);
+      if (z) {
+        const float4 zz = *reinterpret_cast<const float4*>(z + r * ldz + c4 * 4);
+        g.x *= act_bwd_from_out(zz.x, act, slope); g.y *= act_bwd_from_out(zz.y, act, slope);
+        g.z *= act_bwd_from_out(zz.z, act, slope); g.w *= act_bwd_from_out(zz.w, act, slope);
+      }
+      if (gout) *reinterpret_cast<float4*>(gout + r * ldg + c4 * 4) = g;
+      s1.x += g.x; s1.y += g.y; s1.z += g.z; s1.w += g.w;
+      if (y) {
+        const float4 yy = *reinterpret_cast<const float4*>(y + r * ldy + c4 * 4);
+        s2.x += g.x * (yy.x - mu.x) * is.x; s2.y += g.y * (yy.y - mu.y) * is.y;
+        s2.z += g.z * (yy.z - mu.z) * is.z; s2.w += g.w * (yy.w - mu.w) * is.w;
+      }
+    }
+  }
+  sh[0][rl][cl] = s1;
+  sh[1][rl][cl] = s2;
+  __syncthreads();
+  if (rl == 0 && c4 < C4) {
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+      const float4 a = sh[0][k][cl], b = sh[1][k][cl];
+      s1.x += a.x; s1.y += a.y; s1.z += a.z; s1.w += a.w;
+      s2.x += b.x; s2.y += b.y; s2.z += b.z; s2.w += b.w;
+    }
+    float* pp = partials + static_cast<size_t>(blockIdx.y) * 2 * ldp;
+    *reinterpret_cast<float4*>(pp + c4 * 4) = s1;
+    *reinterpret_cast<float4*>(pp + ldp + c4 * 4) = s2;
+  }
+}
+// out[k][c] = sum_i partials[i][k][c]  (k = 0..nk-1), fp64 accumulate
+__global__ void partials_sum_kernel(const float* __restrict__ partials, int nparts, int ldp, int C, int nk,
+                                    float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nk * C) return;
+  const int k = i / C, ch = i - k * C;
+  double s = 0.0;
+  for (int pidx = 0; pidx < nparts; ++pidx) s += partials[(static_cast<size_t>(pidx) * nk + k) * ldp + ch];
+  out[i] = static_cast<float>(s);
+}
+
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ dz, int lddz, const float* __restrict__ z, int ldz,
+                                    const float* __restrict__ y, int ldy, const float* __restrict__ mean,
+                                    const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                    const float* __restrict__ sums, float inv_count, long long rows, int C4, int act,
+                                    float slope, float* __restrict__ dy, int lddy, float* __restrict__ dres,
+                                    int lddres) {
+  const long long total = rows * C4;
+  const int C = C4 * 4;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / C4;
+    const int c = static_cast<int>(i - r * C4) * 4;
+    float4 g = *reinterpret_cast<const float4*>(dz + r * lddz + c);
+    if (z) {
+      const float4 zz = *reinterpret_cast<const float4*>(z + r * ldz + c);
+      g.x *= act_bwd_from_out(zz.x, act, slope); g.y *= act_bwd_from_out(zz.y, act, slope);
+      g.z *= act_bwd_from_out(zz.z, act, slope); g.w *= act_bwd_from_out(zz.w, act, slope);
+    }
+    if (dres) *reinterpret_cast<float4*>(dres + r * lddres + c) = g;
+    const float4 yy = *reinterpret_cast<const float4*>(y + r * ldy + c);
+    const float4 mu = *reinterpret_cast<const float4*>(mean + c);
+    const float4 is = *reinterpret_cast<const float4*>(invstd + c);
+    const float4 ga = gamma ? *reinterpret_cast<const float4*>(gamma + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+    const float4 sg = *reinterpret_cast<const float4*>(sums + c);
+    const float4 sgx = *reinterpret_cast<const float4*>(sums + C + c);
+    float4 o;
+    o.x = ga.x * is.x * (g.x - sg.x * inv_count - (yy.x - mu.x) * is.x * sgx.x * inv_count);
+    o.y = ga.y * is.y * (g.y - sg.y * inv_count - (yy.y - mu.y) * is.y * sgx.y * inv_count);
+    o.z = ga.z * is.z * (g.z - sg.z * inv_count - (yy.z - mu.z) * is.z * sgx.z * inv_count);
+    o.w = ga.w * is.w * (g.w - sg.w * inv_count - (yy.w - mu.w) * is.w * sgx.w * inv_count);
+    *reinterpret_cast<float4*>(dy + r * lddy + c) = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ pooling
+__global__ void maxpool_fwd_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int ldy,
+                                   int* __restrict__ idx, int n, int h, int w, int C4, int k, int stride, int pad,
+                                   int ho, int wo) {
+  const long long total = static_cast<long long>(n) * ho * wo * C4;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long pix = i / C4;
+    const int c = static_cast<int>(i - pix * C4) * 4;
+    const int ox = static_cast<int>(pix % wo);
+    const int oy = static_cast<int>((pix / wo) % ho);
+    const int img = static_cast<int>(pix / (static_cast<long long>(wo) * ho));
+    float4 best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    int4 bi = make_int4(-1, -1, -1, -1);
+    for (int ky = 0; ky < k; ++ky) {
+      const int iy = oy * stride - pad + ky;
+      if (iy < 0 || iy >= h) continue;
+      for (int kx = 0; kx < k; ++kx) {
+        const int ix = ox * stride - pad + kx;
+        if (ix < 0 || ix >= w) continue;
+        const int ip = (img * h + iy) * w + ix;
+        const float4 v = *reinterpret_cast<const float4*>(x + static_cast<long long>(ip) * ldx + c);
+        if (v.x > best.x || bi.x < 0) { best.x = v.x; bi.x = ip; }
+        if (v.y > best.y || bi.y < 0) { best.y = v.y; bi.y = ip; }
+        if (v.z > best.z || bi.z < 0) { best.z = v.z; bi.z = ip; }
+        if (v.w > best.w || bi.w < 0) { best.w = v.w; bi.w = ip; }
+      }
+    }
+    *reinterpret_cast<float4*>(y + pix * ldy + c) = best;
+    if (idx) *reinterpret_cast<int4*>(idx + pix * (C4 * 4) + c) = bi;
+  }
+}
+__global__ void maxpool_bwd_kernel(const float* __restrict__ dy, int lddy, const int* __restrict__ idx,
+                                   float* __restrict__ dx, int lddx, long long opix, int C) {
+  const long long total = opix * C;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long pix = i / C;
+    const int c = static_cast<int>(i - pix * C);
+    const int ip = idx[i];
+    if (ip >= 0) atomicAdd(dx + static_cast<long long>(ip) * lddx + c, dy[pix * lddy + c]);
+  }
+}
+// out[img][c] = scale * sum_p x[img][p][c];  grid = (ceil(C/128), n), block = (128 channels? no: 32 x 8)
+__global__ void pixel_sum_kernel(const float* __restrict__ x, int ldx, float* __restrict__ out, int hw, int C,
+                                 float scale) {
+  __shared__ float sh[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int img = blockIdx.y;
+  float s = 0.f;
+  if (c < C)
+    for (int pidx = threadIdx.y; pidx < hw; pidx += 8) s += x[(static_cast<long long>(img) * hw + pidx) * ldx + c];
+  sh[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    for (int k = 1; k < 8; ++k) s += sh[k][threadIdx.x];
+    out[static_cast<long long>(img) * C + c] = s * scale;
+  }
+}
+// global max over pixels with argmax (AdaptiveMaxPool2d((1,1)), models/audio/audio_network.py:24)
+__global__ void pixel_max_kernel(const float* __restrict__ x, int ldx, float* __restrict__ out, int* __restrict__ arg,
+                                 int hw, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int img = blockIdx.y;
+  if (c >= C) return;
+  float best = -INFINITY;
+  int bi = 0;
+  for (int pidx = 0; pidx < hw; ++pidx) {
+    const float v = x[(static_cast<long long>(img) * hw + pidx) * ldx + c];
+    if (v > best || pidx == 0) { best = v; bi = pidx; }
+  }
+  out[static_cast<long long>(img) * C + c] = best;
+  arg[static_cast<long long>(img) * C + c] = bi;
+}
+__global__ void pixel_max_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ arg,
+                                     float* __restrict__ dx, int lddx, int hw, int C, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * C) return;
+  const int img = i / C, c = i - img * C;
+  dx[(static_cast<long long>(img) * hw + arg[i]) * lddx + c] = dout[i];
+}
+// dx[img][p][c] (+)= scale * dout[img][c]
+__global__ void pixel_bcast_kernel(const float* __restrict__ dout, float* __restrict__ dx, int lddx, int hw, int C4,
+                                   long long rows, float scale, int accumulate) {
+  const long long total = rows * C4;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / C4;
+    const int c = static_cast<int>(i - r * C4) * 4;
+    const long long img = r / hw;
+    const float4 g = *reinterpret_cast<const float4*>(dout + img * (C4 * 4) + c);
+    float4* d = reinterpret_cast<float4*>(dx + r * lddx + c);
+    float4 o = make_float4(g.x * scale, g.y * scale, g.z * scale, g.w * scale);
+    if (accumulate) {
+      const float4 a = *d;
+      o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+    }
+    *d = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ bilinear
+// Source index exactly as ATen's area_pixel_compute_source_index (fp32 arithmetic).
+struct Lerp { int i0, i1; float w0, w1; };
+__device__ __forceinline__ Lerp lerp_index(int dst, int in_size, float scale, int align_corners) {
+  float src;
+  if (align_corners) {
+    src = scale * dst;
+  } else {
+    src = scale * (dst + 0.5f) - 0.5f;
+    if (src < 0.f) src = 0.f;
+  }
+  Lerp l;
+  l.i0 = static_cast<int>(src);
+  if (l.i0 > in_size - 1) l.i0 = in_size - 1;
+  l.i1 = l.i0 + (l.i0 < in_size - 1 ? 1 : 0);
+  l.w1 = src - l.i0;
+  l.w0 = 1.f - l.w1;
+  return l;
+}
+__host__ __device__ inline float lerp_scale(int in_size, int out_size, int align_corners) {
+  if (align_corners) return out_size > 1 ? static_cast<float>(in_size - 1) / (out_size - 1) : 0.f;
+  return static_cast<float>(in_size) / out_size;
+}
+
+__global__ void bilinear_fwd_nhwc_kernel(const float* __restrict__ x, int ldx, int hin, int win,
+                                         float* __restrict__ y, int ldy, int hout, int wout, int n, int C4,
+                                         int align, float sh, float sw) {
+  const long long total = static_cast<long long>(n) * hout * wout * C4;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long pix = i / C4;
+    const int c = static_cast<int>(i - pix * C4) * 4;
+    const int ox = static_cast<int>(pix % wout);
+    const int oy = static_cast<int>((pix / wout) % hout);
+    const long long img = pix / (static_cast<long long>(wout) * hout);
+    const Lerp ly = lerp_index(oy, hin, sh, align), lx = lerp_index(ox, win, sw, align);
+    const float* base = x + img * hin * win * ldx + c;
+    const float4 a = *reinterpret_cast<const float4*>(base + (static_cast<long long>(ly.i0) * win + lx.i0) * ldx);
+    const float4 b = *reinterpret_cast<const float4*>(base + (static_cast<long long>(ly.i0) * win + lx.i1) * ldx);
+    const float4 cc = *reinterpret_cast<const float4*>(base + (static_cast<long long>(ly.i1) * win + lx.i0) * ldx);
+    const float4 d = *reinterpret_cast<const float4*>(base + (static_cast<long long>(ly.i1) * win + lx.i1) * ldx);
+    float4 o;
+    o.x = ly.w0 * (lx.w0 * a.x + lx.w1 * b.x) + ly.w1 * (lx.w0 * cc.x + lx.w1 * d.x);
+    o.y = ly.w0 * (lx.w0 * a.y + lx.w1 * b.y) + ly.w1 * (lx.w0 * cc.y + lx.w1 * d.y);
+    o.z = ly.w0 * (lx.w0 * a.z + lx.w1 * b.z) + ly.w1 * (lx.w0 * cc.z + lx.w1 * d.z);
+    o.w = ly.w0 * (lx.w0 * a.w + lx.w1 * b.w) + ly.w1 * (lx.w0 * cc.w + lx.w1 * d.w);
+    *reinterpret_cast<float4*>(y + pix * ldy + c) = o;
+  }
+}
+// NHWC (low-res logits) -> NCHW full-resolution prediction; thread per output pixel, loop over classes
+__global__ void bilinear_fwd_nchw_kernel(const float* __restrict__ x, int ldx, int hin, int win,
+                                         float* __restrict__ y, int hout, int wout, int n, int C, int align, float sh,
+                                         float sw) {
+  const long long total = static_cast<long long>(n) * hout * wout;
+  const long long plane = static_cast<long long>(hout) * wout;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ox = static_cast<int>(i % wout);
+    const int oy = static_cast<int>((i / wout) % hout);
+    const long long img = i / plane;
+    const Lerp ly = lerp_index(oy, hin, sh, align), lx = lerp_index(ox, win, sw, align);
+    const float* base = x + img * hin * win * ldx;
+    const float* pa = base + (static_cast<long long>(ly.i0) * win + lx.i0) * ldx;
+    const float* pb = base + (static_cast<long long>(ly.i0) * win + lx.i1) * ldx;
+    const float* pc = base + (static_cast<long long>(ly.i1) * win + lx.i0) * ldx;
+    const float* pd = base + (static_cast<long long>(ly.i1) * win + lx.i1) * ldx;
+    float* o = y + img * C * plane + static_cast<long long>(oy) * wout + ox;
+    for (int ch = 0; ch < C; ++ch)
+      o[ch * plane] = ly.w0 * (lx.w0 * pa[ch] + lx.w1 * pb[ch]) + ly.w1 * (lx.w0 * pc[ch] + lx.w1 * pd[ch]);
+  }
+}
+// Gather-form backward (deterministic, no atomics): every low-res element collects from the output pixels whose
+// 2x2 footprint touches it.  dy is NHWC (ld) or NCHW (nchw=1).  Images >= n_valid have an all-zero gradient.
+__global__ void bilinear_bwd_kernel(const float* __restrict__ dy, int lddy, int hout, int wout,
+                                    float* __restrict__ dx, int lddx, int hin, int win, int n, int C, int align,
+                                    float sh, float sw, int nchw, int n_valid) {
+  const long long total = static_cast<long long>(n) * hin * win * C;
+  const long long plane = static_cast<long long>(hout) * wout;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    int ch, ix, iy;
+    long long img;
+    if (nchw) {  // threads vary over x fastest for the NCHW source
+      ix = static_cast<int>(i % win);
+      iy = static_cast<int>((i / win) % hin);
+      ch = static_cast<int>((i / (static_cast<long long>(win) * hin)) % C);
+      img = i / (static_cast<long long>(win) * hin * C);
+    } else {
+      ch = static_cast<int>(i % C);
+      ix = static_cast<int>((i / C) % win);
+      iy = static_cast<int>((i / (static_cast<long long>(C) * win)) % hin);
+      img = i / (static_cast<long long>(C) * win * hin);
+    }
+    float acc = 0.f;
+    if (img < n_valid) {
+      // candidate output rows / cols: source coordinate within (i-1, i+1)
+      int y_lo, y_hi, x_lo, x_hi;
+      if (align) {
+        y_lo = sh > 0.f ? static_cast<int>(floorf((iy - 1) / sh)) : 0;
+        y_hi = sh > 0.f ? static_cast<int>(ceilf((iy + 1) / sh)) : hout - 1;
+        x_lo = sw > 0.f ? static_cast<int>(floorf((ix - 1) / sw)) : 0;
+        x_hi = sw > 0.f ? static_cast<int>(ceilf((ix + 1) / sw)) : wout - 1;
+      } else {
+        y_lo = static_cast<int>(floorf((iy - 1 + 0.5f) / sh - 0.5f));
+        y_hi = static_cast<int>(ceilf((iy + 1 + 0.5f) / sh - 0.5f));
+        x_lo = static_cast<int>(floorf((ix - 1 + 0.5f) / sw - 0.5f));
+        x_hi = static_cast<int>(ceilf((ix + 1 + 0.5f) / sw - 0.5f));
+      }
+      y_lo = max(y_lo - 1, 0); y_hi = min(y_hi + 1, hout - 1);
+      x_lo = max(x_lo - 1, 0); x_hi = min(x_hi + 1, wout - 1);
+      for (int oy = y_lo; oy <= y_hi; ++oy) {
+        const Lerp ly = lerp_index(oy, hin, sh, align);
+        const float wy = (ly.i0 == iy ? ly.w0 : 0.f) + (ly.i1 == iy ? ly.w1 : 0.f);
+        if (wy == 0.f) continue;
+        for (int ox = x_lo; ox <= x_hi; ++ox) {
+          const Lerp lx = lerp_index(ox, win, sw, align);
+          const float wx = (lx.i0 == ix ? lx.w0 : 0.f) + (lx.i1 == ix ? lx.w1 : 0.f);
+          if (wx == 0.f) continue;
+          const float g = nchw ? dy[(img * C + ch) * plane + static_cast<long long>(oy) * wout + ox]
+                               : dy[(img * plane + static_cast<long long>(oy) * wout + ox) * lddy + ch];
+          acc += wy * wx * g;
+        }
+      }
+    }
+    dx[((img * hin + iy) * win + ix) * static_cast<long long>(lddx) + ch] = acc;
+  }
+}
+
+}  // namespace cavp
+
+using namespace cavp;
+#define ST(s) static_cast<cudaStream_t>(s)
+
+extern "C" int cavp_zero(void* ptr, long long bytes, void* stream) {
+  return static_cast<int>(cudaMemsetAsync(ptr, 0, static_cast<size_t>(bytes), ST(stream)));
+}
+extern "C" int cavp_nchw_to_nhwc(const float* src, float* dst, int n, int c, int hw, int cpad, void* stream) {
+  nchw_to_nhwc_kernel<<<grid_for(static_cast<long long>(n) * hw, 256), 256, 0, ST(stream)>>>(src, dst, n, c, hw, cpad);
+  CAVP_LAUNCH_CHECK();
+}
+extern "C" int cavp_nhwc_to_nchw(const float* src, float* dst, int n, int c, int hw, int ld, void* stream) {
+  nhwc_to_nchw_kernel<<<grid_for(static_cast<long long>(n) * hw, 256), 256, 0, ST(stream)>>>(src, dst, n, c, hw, ld);
+  CAVP_LAUNCH_CHECK();
+}
+extern "C" int cavp_transpose(const float* src, float* dst, int rows, int cols, long long src_ld, long long dst_ld,
+                              int batch, long long src_bs, long long dst_bs, void* stream) {
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32, batch), block(32, 8);
+  transpose_kernel<<<grid, block, 0, ST(stream)>>>(src, dst, rows, cols, src_ld, dst_ld, src_bs, dst_bs);
+  CAVP_LAUNCH_CHECK();
+}
+extern "C" int cavp_add_inplace(float* dst, const float* src, long long n, float alpha, void* stream) {
+  if (n & 3) return CAVP_ERR_ALIGN;
+  add_inplace_kernel<<<grid_for(n / 4, 256), 256, 0, ST(stream)>>>(dst, src, n / 4, alpha);
+  CAVP_LAUNCH_CHECK();
+}
+extern "C" int cavp_gather_rows(const float* src, const long long* idx, float* dst, int nrows, int c,
+                                int accumulate_scatter, void* stream) {
+  gather_rows_kernel<<<nrows, 128, 0, ST(stream)>>>(src, idx, dst, nrows, c, accumulate_scatter);
+  CAVP_LAUNCH_CHECK();
+}
+extern "C" int cavp_bn_finalize(const float* partials, int nparts, int ldstat, int C, double count, const float* gamma,
+                                const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                                float* mean_out, float* invstd_out, float* scale_out, float* shift_out, double* sums_io,
+                                int sums_mode, void* stream) {
+  const int threads = 256, warps_per_block = threads / 32;
+  bn_finalize_kernel<<<(C + warps_per_block - 1) / warps_per_block, threads, 0, ST(stream)>>>(
+      partials, nparts, ldstat, C, count, gamma, beta, running_mean, running_var, momentum, eps, mean_out, invstd_out,
+      scale_out, shift_out, sums_io, sums_mode);
+  CAVP_LAUNCH_CHECK();
+}
+extern "C" int cavp_bn_eval_coeffs(const float* gamma, const float* beta, const float* rm, const float* rv, float eps,
+                                   int C, float* scale, float* shift, void* stream) {
+  bn_eval_coeffs_kernel<<<(C + 255) / 256, 256, 0, ST(stream)>>>(gamma, beta, rm, rv, eps, C, scale, shift);
+  CAVP_LAUNCH_CHECK();
+}
+extern "C" int cavp_bn_apply(const float* y, int ldy, const float* scale, const float* shift, const float* res, int ldr,
+                             float* out, int ldo, long long rows, int C, int act, float slope, void* stream) {
+  if ((C & 3) || (ldy & 3) || (ldo & 3) || (res && (ldr & 3))) return CAVP_ERR_ALIGN;
+  bn_apply_kernel<<<grid_for(rows * (C / 4), 256), 256, 0, ST(stream)>>>(y, ldy, scale, shift, res, ldr, out, ldo, rows,
+                                                                         C / 4, act, slope);
+  CAVP_LAUNCH_CHECK();
+}
+extern "C" int cavp_colreduce(const float* dz, int lddz, const float* z, int ldz, const float* y, int ldy,
+                              const float* mean, const float* invstd, long long rows, int C, int act, float slope,
+                              float* gout, int ldg, float* partials, int ldp, int nblk, void* stream) {
+  if ((C & 3) || (lddz & 3) || (z && (ldz & 3)) || (y && (ldy & 3)) || (gout && (ldg & 3)) || (ldp & 3))
+    return CAVP_ERR_ALIGN;
+  dim3 grid((C / 4 + 63) / 64, nblk);
+  colreduce_kernel<<<grid, 256, 0, ST(stream)>>>(dz, lddz, z, ldz, y, ldy, mean, invstd, rows, C / 4, act, slope, gout,
+                                                 ldg, partials, ldp);
+  CAVP_LAUNCH_CHECK();
+}
+extern "C" int cavp_partials_sum(const float* partials, int nparts, int ldp, int C, int nk, float* out, void* stream) {
+  partials_sum_kernel<<<(nk * C + 127) / 128, 128, 0, ST(stream)>>>(partials, nparts, ldp, C, nk, out);
+  CAVP_LAUNCH_CHECK();
+}
+extern "C" int cavp_bn_bwd_apply(const float* dz, int lddz, const float* z, int ldz, const float* y, int ldy,
+                                 const float* mean, const float* invstd, const float* gamma, const float* sums,
+                                 float inv_count, long long rows, int C, int act, float slope, float* dy, int lddy,
+                                 float* dres, int lddres, void* stream) {
+  if ((C & 3) || (lddz & 3) || (ldy & 3) || (lddy & 3)) return CAVP_ERR_ALIGN;
+  bn_bwd_apply_kernel<<<grid_for(rows * (C / 4), 256), 256, 0, ST(stream)>>>(
+      dz, lddz, z, ldz, y, ldy, mean, invstd, gamma, sums, inv_count, rows, C / 4, act, slope, dy, lddy, dres, lddres);
+  CAVP_LAUNCH_CHECK();
+}
+extern "C" int cavp_maxpool_fwd(const float* x, int ldx, float* y, int ldy, int* idx, int n, int h, int w, int c, int k,
+                                int stride, int pad, int ho, int wo, void* stream) {
+  if ((c & 3) || (ldx & 3) || (ldy & 3)) return CAVP_ERR_ALIGN;
+  maxpool_fwd_kernel<<<grid_for(static_cast<long long>(n) * ho * wo * (c / 4), 256), 256, 0, ST(stream)>>>(
+      x, ldx, y, ldy, idx, n, h, w, c / 4, k, stride, pad, ho, wo);
+  CAVP_LAUNCH_CHECK();
+}
+extern "C" int cavp_maxpool_bwd(const float* dy, int lddy, const int* idx, float* dx, int lddx, long long opix, int c,
+                                void* stream) {
+  maxpool_bwd_kernel<<<grid_for(opix * c, 256), 256, 0, ST(stream)>>>(dy, lddy, idx, dx, lddx, opix, c);
+  CAVP_LAUNCH_CHECK();
+}
+extern "C" int cavp_pixel_sum(const float* x, int ldx, float* out, int n, int hw, int c, float scale, void* stream) {
+  dim3 grid((c + 31) / 32, n), block(32, 8);
+  pixel_sum_kernel<<<grid, block, 0, ST(stream)>>>(x, ldx, out, hw, c, scale);
+  CAVP_LAUNCH_CHECK();
+}
+extern "C" int cavp_pixel_max(const float* x, int ldx, float* out, int* arg, int n, int hw, int c, void* stream) {
+  dim3 grid((c + 127) / 128, n);
+  pixel_max_kernel<<<grid, 128, 0, ST(stream)>>>(x, ldx, out, arg, hw, c);
+  CAVP_LAUNCH_CHECK();
+}
+extern "C" int cavp_pixel_max_bwd(const float* dout, const int* arg, float* dx, int lddx, int n, int hw, int c,
+                                  void* stream) {
+  pixel_max_bwd_kernel<<<(n * c + 255) / 256, 256, 0, ST(stream)>>>(dout, arg, dx, lddx, hw, c, n);
+  CAVP_LAUNCH_CHECK();
+}
+extern "C" int cavp_pixel_bcast(const float* dout, float* dx, int lddx, int n, int hw, int c, float scale,
+                                int accumulate, void* stream) {
+  if ((c & 3) || (lddx & 3)) return CAVP_ERR_ALIGN;
+  const long long rows = static_cast<long long>(n) * hw;
+  pixel_bcast_kernel<<<grid_for(rows * (c / 4), 256), 256, 0, ST(stream)>>>(dout, dx, lddx, hw, c / 4, rows, scale,
+                                                                            accumulate);
+  CAVP_LAUNCH_CHECK();
+}
+extern "C" int cavp_bilinear_fwd(const float* x, int ldx, int hin, int win, float* y, int ldy, int hout, int wout,
+                                 int n, int c, int align_corners, int nchw_out, void* stream) {
+  const float sh = lerp_scale(hin, hout, align_corners), sw = lerp_scale(win, wout, align_corners);
+  if (nchw_out) {
+    bilinear_fwd_nchw_kernel<<<grid_for(static_cast<long long>(n) * hout * wout, 256, 16), 256, 0, ST(stream)>>>(
+        x, ldx, hin, win, y, hout, wout, n, c, align_corners, sh, sw);
+  } else {
+    if ((c & 3) || (ldx & 3) || (ldy & 3)) return CAVP_ERR_ALIGN;
+    bilinear_fwd_nhwc_kernel<<<grid_for(static_cast<long long>(n) * hout * wout * (c / 4), 256, 16), 256, 0,
+                               ST(stream)>>>(x, ldx, hin, win, y, ldy, hout, wout, n, c / 4, align_corners, sh, sw);
+  }
+  CAVP_LAUNCH_CHECK();
+}
+extern "C" int cavp_bilinear_bwd(const float* dy, int lddy, int hout, int wout, float* dx, int lddx, int hin, int win,
+                                 int n, int c, int align_corners, int nchw_in, int n_valid, void* stream) {
+  const float sh = lerp_scale(hin, hout, align_corners), sw = lerp_scale(win, wout, align_corners);
+  bilinear_bwd_kernel<<<grid_for(static_cast<long long>(n) * hin * win * c, 256, 16), 256, 0, ST(stream)>>>(
+      dy, lddy, hout, wout, dx, lddx, hin, win, n, c, align_corners, sh, sw, nchw_in, n_valid);
+  CAVP_LAUNCH_CHECK();
+}

@@ -1,0 +1,472 @@
+// Implicit-GEMM convolution / linear kernels on tcgen05 (sm_100a), fp32 in HBM, TF32 tensor-core products.
+//
+// Data layout: activations are NHWC with an explicit pixel stride `ld` (so channel slices of a concat buffer are
+// ordinary operands); weights are [Cout][R][S][Cin] (= K-major rows of length K = R*S*Cin).
+//
+//   MODE_ROW  : D[M x N] = A[M x K] * B[N x K]^T, both operands K-major in shared memory.  A is gathered on the fly
+//               (im2col for forward, the transposed-stride gather for dgrad), B is the weight matrix.
+//               Forward conv / linear / dgrad (with pre-transposed weights) all run through it.
+//   MODE_WGRAD: dW[Cout x K] = dY[P x Cout]^T * im2col(X)[P x K]; the reduction runs over pixels, so both operands are
+//               MN-major in shared memory (no transposes in HBM).
+//
+// CTA = 8 producer/epilogue warps + 1 MMA warp.  The two producer groups (4 warps each) alternate k-blocks:
+// global -> registers -> TF32 hi/lo split -> swizzled shared memory -> fence.proxy.async -> mbarrier.  One elected
+// thread issues tcgen05.mma (M=128, N=BN, K=8) into TMEM; tcgen05.commit releases the stage.
+//
+// Precision (DESIGN.md "precision"): PREC=1 is plain TF32.  PREC=2 is the fp32-parity mode: three MMAs per k-step
+// (hi*hi + lo*hi + hi*lo) AND accumulator promotion - the tensor core adds into TMEM with truncation, which biases
+// long accumulation chains (measured: ~8e-9*K relative), so every 2 k-blocks (64 K-elements) the partial sum is
+// pulled out of a 4-deep TMEM ring with tcgen05.ld and added, round-to-nearest, into fp32 registers by the
+// producer warps while their next global loads are in flight.
+#pragma once
+#include "ptx.cuh"
+
+namespace cavp {
+
+constexpr int BM = 128;        // tile rows = TMEM lanes
+constexpr int BK = 32;         // fp32 per k-block = one 128-byte swizzle row
+constexpr int UMMA_K = 8;      // tf32
+constexpr int PRODUCER_THREADS = 256;
+constexpr int GROUP_THREADS = 128;
+constexpr int CTA_THREADS = PRODUCER_THREADS + 32;
+constexpr int MODE_ROW = 0;
+constexpr int MODE_WGRAD = 1;
+
+enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2, ACT_GELU = 3, ACT_SIGMOID = 4 };
+
+struct IgemmParams {
+  // MODE_ROW: x = A source (NHWC, pixel stride ldx), w = B [Ncols][ldw] K-major, y = D [M][ldy]
+  // MODE_WGRAD: x = NHWC source of the im2col operand, w = dY [P][ldw] (Cout columns), y = dW [Cout][K]
+  const float* x;
+  const float* w;
+  float* y;
+  float* y_pre;        // optional copy of D before the activation (same ld)
+  const float* scale;  // optional per-column scale (eval-mode BN)
+  const float* shift;  // optional per-column shift / bias
+  const float* res;    // optional residual [res_mod or M][ldr], added before the activation
+  float* stats;        // optional per-(m_tile, warp-quarter) column partial sums: [m_tiles*4][2][ldstat]
+  int Nimg, Hs, Ws, C, ldx;
+  int Ho, Wo;
+  int R, S, stride, pad, dil;
+  int dgrad;
+  int M, Ncols, K, ldw, ldy, ldr, res_mod, ldstat;
+  int red_len;  // length of the reduction dimension (K for MODE_ROW, P pixels for MODE_WGRAD)
+  int act;
+  float slope;
+  int n_tiles, num_kb, splits;
+  FastDiv div_howo, div_wo, div_c, div_s;
+};
+
+template <int BN, int PREC>
+struct TileCfg {
+  static constexpr bool PROMOTE = (PREC == 2);
+  static constexpr int NBUF = PROMOTE ? 4 : 1;
+  static constexpr int A_BYTES = BM * 128;
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * PREC;
+  static constexpr int STAGES = (PREC == 2) ? (BN >= 128 ? 3 : 4) : 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = NBUF * BN < 32 ? 32 : NBUF * BN;
+  static constexpr int HALF = BN / 2;  // accumulator columns owned by one epilogue thread
+};
+
+__device__ __forceinline__ float apply_act(float v, int act, float slope) {
+  switch (act) {
+    case ACT_RELU: return fmaxf(v, 0.f);
+    case ACT_LEAKY: return v > 0.f ? v : v * slope;
+    case ACT_GELU: return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+    case ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+    default: return v;
+  }
+}
+
+template <int PREC>
+__device__ __forceinline__ void store_split(uint32_t hi_addr, uint32_t lo_addr, const float4& v) {
+  const float h0 = tf32_rn(v.x), h1 = tf32_rn(v.y), h2 = tf32_rn(v.z), h3 = tf32_rn(v.w);
+  st_shared_v4(hi_addr, h0, h1, h2, h3);
+  if (PREC == 2) st_shared_v4(lo_addr, tf32_rn(v.x - h0), tf32_rn(v.y - h1), tf32_rn(v.z - h2), tf32_rn(v.w - h3));
+}
+
+// Column sums of a 32(lanes) x 32(registers) block: after the call lane j holds sum_i v_i[j] in v[0].
+__device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = up ? v[i] : v[i + s];
+      const float keep = up ? v[i + s] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+template <int BN, int PREC, int MODE>
+__global__ void __launch_bounds__(CTA_THREADS, 1) igemm_kernel(const IgemmParams p) {
+  using Cfg = TileCfg<BN, PREC>;
+  constexpr bool PROMOTE = Cfg::PROMOTE;
+  constexpr int NBUF = Cfg::NBUF;
+  constexpr int HALF = Cfg::HALF;
+  static_assert(BN == 64 || BN == 128, "BN must be 64 or 128");
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_aligned = smem_raw + (smem_base - smem_u32(smem_raw));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_aligned + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;                             // [STAGES]  producers -> MMA
+  uint64_t* empty_bar = bars + Cfg::STAGES;              // [STAGES]  MMA -> producers
+  uint64_t* accf_bar = bars + 2 * Cfg::STAGES;           // [NBUF]    MMA -> promotion
+  uint64_t* acce_bar = bars + 2 * Cfg::STAGES + NBUF;    // [NBUF]    promotion -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 2 * NBUF);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+
+  const int tile = blockIdx.x;
+  const int n_tile = tile % p.n_tiles;
+  const int m_tile = tile / p.n_tiles;
+  const int m0 = m_tile * BM;
+  const int n0 = n_tile * BN;
+  // split range of k-blocks (over the reduction dimension) for this CTA
+  const int split = blockIdx.y;
+  const int kb_begin = static_cast<int>((static_cast<long long>(p.num_kb) * split) / p.splits);
+  const int kb_end = static_cast<int>((static_cast<long long>(p.num_kb) * (split + 1)) / p.splits);
+  const int nkb = kb_end - kb_begin;
+
+  if (tid == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&full_bar[s], GROUP_THREADS);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < NBUF; ++b) {
+      mbar_init(&accf_bar[b], 1);
+      mbar_init(&acce_bar[b], PRODUCER_THREADS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 8) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 8) {
+    // ===================================================== producers (+ promotion + epilogue)
+    const int group = warp >> 2;
+    const int gtid = tid & (GROUP_THREADS - 1);
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    float acc[HALF];
+#pragma unroll
+    for (int j = 0; j < HALF; ++j) acc[j] = 0.f;
+
+    auto promote = [&](int u) {
+      const int b = PROMOTE ? (u & (NBUF - 1)) : 0;
+      mbar_wait(&accf_bar[b], PROMOTE ? ((u / NBUF) & 1) : 0);
+      tc_fence_after();
+#pragma unroll
+      for (int cgrp = 0; cgrp < HALF / 32; ++cgrp) {
+        float v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                      static_cast<uint32_t>(b * BN + group * HALF + cgrp * 32),
+                  v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[cgrp * 32 + j] += v[j];
+      }
+      if (PROMOTE) {
+        tc_fence_before();
+        mbar_arrive(&acce_bar[b]);
+      }
+    };
+
+    // ---- per-thread operand addressing
+    // MODE_ROW  : chunk column c (16 B) of the 128-byte k-row; rows r0 + 16 i
+    // MODE_WGRAD: chunk cc (16 B) along MN (atom = cc>>3); k-rows (pixels) rr + 4 i
+    const int c = gtid & 7;
+    const int r0 = gtid >> 3;
+    const uint32_t swz = static_cast<uint32_t>((c ^ (r0 & 7)) << 4);
+    const int cc = gtid & 31;
+    const int rr = gtid >> 5;
+    int nb[8], yx[8];  // yx packs (ybase + 0x4000) << 16 | (xbase + 0x4000)
+    // wgrad per-thread constants
+    int wg_co = 0, wg_dy = 0, wg_dx = 0;
+    uint32_t wg_ci = 0;
+    bool wg_co_ok = false, wg_j_ok = false;
+    if (MODE == MODE_ROW) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int m = m0 + r0 + 16 * i;
+        if (m < p.M) {
+          uint32_t n, rem, oy, ox;
+          p.div_howo.divmod(static_cast<uint32_t>(m), n, rem);
+          p.div_wo.divmod(rem, oy, ox);
+          nb[i] = static_cast<int>(n) * p.Hs * p.Ws;
+          int ybase, xbase;
+          if (p.dgrad) {
+            ybase = static_cast<int>(oy) + p.pad;
+            xbase = static_cast<int>(ox) + p.pad;
+          } else {
+            ybase = static_cast<int>(oy) * p.stride - p.pad;
+            xbase = static_cast<int>(ox) * p.stride - p.pad;
+          }
+          yx[i] = ((ybase + 0x4000) << 16) | (xbase + 0x4000);
+        } else {
+          nb[i] = -1;
+          yx[i] = 0;
+        }
+      }
+    } else {
+      wg_co = m0 + cc * 4;
+      wg_co_ok = wg_co < p.M;
+      const int j = n0 + cc * 4;
+      wg_j_ok = (cc * 4 < BN) && j < p.Ncols;
+      uint32_t tap, ky, kx;
+      p.div_c.divmod(static_cast<uint32_t>(wg_j_ok ? j : 0), tap, wg_ci);
+      p.div_s.divmod(tap, ky, kx);
+      wg_dy = static_cast<int>(ky) * p.dil - p.pad;
+      wg_dx = static_cast<int>(kx) * p.dil - p.pad;
+    }
+
+    const int npairs = (nkb + 1) >> 1;
+    for (int u = 0; u < npairs; ++u) {
+      const int it = 2 * u + group;
+      const bool active = it < nkb;
+      const int s = it % Cfg::STAGES;
+      float4 va[8];
+      float4 vb[8];
+      if (active) {
+        mbar_wait(&empty_bar[s], (((it / Cfg::STAGES) & 1) ^ 1));
+        if (MODE == MODE_ROW) {
+          const int k = (kb_begin + it) * BK + c * 4;
+          const bool kvalid = k < p.K;
+          uint32_t tap, ci, ky, kx;
+          p.div_c.divmod(static_cast<uint32_t>(kvalid ? k : 0), tap, ci);
+          p.div_s.divmod(tap, ky, kx);
+          const int dy = static_cast<int>(ky) * p.dil;
+          const int dx = static_cast<int>(kx) * p.dil;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            int iy, ix;
+            bool ok = kvalid && nb[i] >= 0;
+            const int ybase = (yx[i] >> 16) - 0x4000, xbase = (yx[i] & 0xFFFF) - 0x4000;
+            if (p.dgrad) {
+              iy = ybase - dy;
+              ix = xbase - dx;
+              if (p.stride > 1) {
+                ok = ok && iy >= 0 && ix >= 0 && (iy % p.stride) == 0 && (ix % p.stride) == 0;
+                iy /= p.stride;
+                ix /= p.stride;
+              }
+            } else {
+              iy = ybase + dy;
+              ix = xbase + dx;
+            }
+            ok = ok && static_cast<unsigned>(iy) < static_cast<unsigned>(p.Hs) &&
+                 static_cast<unsigned>(ix) < static_cast<unsigned>(p.Ws);
+            va[i] = ok ? ldg_nc_v4(p.x + static_cast<size_t>(nb[i] + iy * p.Ws + ix) * p.ldx + ci)
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int j = 0; j < BN / 16; ++j) {
+            const int n = n0 + r0 + 16 * j;
+            vb[j] = (kvalid && n < p.Ncols) ? ldg_nc_v4(p.w + static_cast<size_t>(n) * p.ldw + k)
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        } else {
+          const int pix0 = (kb_begin + it) * BK;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int pix = pix0 + rr + 4 * i;
+            const bool pok = pix < p.red_len;
+            va[i] = (pok && wg_co_ok) ? ldg_nc_v4(p.w + static_cast<size_t>(pix) * p.ldw + wg_co)
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+            bool ok = pok && wg_j_ok;
+            uint32_t n = 0, rem, oy = 0, ox = 0;
+            if (ok) {
+              p.div_howo.divmod(static_cast<uint32_t>(pix), n, rem);
+              p.div_wo.divmod(rem, oy, ox);
+            }
+            const int iy = static_cast<int>(oy) * p.stride + wg_dy;
+            const int ix = static_cast<int>(ox) * p.stride + wg_dx;
+            ok = ok && static_cast<unsigned>(iy) < static_cast<unsigned>(p.Hs) &&
+                 static_cast<unsigned>(ix) < static_cast<unsigned>(p.Ws);
+            vb[i] = ok ? ldg_nc_v4(p.x +
+                                   (static_cast<size_t>(n) * p.Hs * p.Ws + static_cast<size_t>(iy) * p.Ws + ix) *
+                                       p.ldx +
+                                   wg_ci)
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+      }
+      if (PROMOTE && u >= 2) promote(u - 2);  // overlaps with the global loads issued above
+      if (active) {
+        const uint32_t stage = smem_base + s * Cfg::STAGE_BYTES;
+        const uint32_t a_hi = stage, a_lo = stage + Cfg::A_BYTES;
+        const uint32_t b_hi = stage + Cfg::A_BYTES * PREC, b_lo = b_hi + Cfg::B_BYTES;
+        if (MODE == MODE_ROW) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint32_t off = static_cast<uint32_t>((r0 + 16 * i) * 128) + swz;
+            store_split<PREC>(a_hi + off, a_lo + off, va[i]);
+          }
+#pragma unroll
+          for (int j = 0; j < BN / 16; ++j) {
+            const uint32_t off = static_cast<uint32_t>((r0 + 16 * j) * 128) + swz;
+            store_split<PREC>(b_hi + off, b_lo + off, vb[j]);
+          }
+        } else {
+          // MN-major tf32 operands use the 128B swizzle with a 32-byte base: atom = 4 k-rows x 128 B, the 32-byte
+          // chunk index is XORed with (k-row & 3).
+          const uint32_t atom_off = static_cast<uint32_t>((cc >> 3) * 4096);
+          const int c16 = cc & 7;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = rr + 4 * i;
+            const uint32_t off = atom_off + static_cast<uint32_t>(r * 128) +
+                                 static_cast<uint32_t>((((c16 >> 1) ^ (r & 3)) << 5) | ((c16 & 1) << 4));
+            store_split<PREC>(a_hi + off, a_lo + off, va[i]);
+            if (cc * 4 < BN) store_split<PREC>(b_hi + off, b_lo + off, vb[i]);
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(&full_bar[s]);
+      }
+    }
+    if (PROMOTE) {
+      for (int u = (npairs > 2 ? npairs - 2 : 0); u < npairs; ++u) promote(u);
+    } else {
+      promote(0);
+    }
+
+    // ===================================================== epilogue from registers
+    const int row = m0 + q * 32 + lane;
+    const bool row_ok = row < p.M;
+    const bool vec_ok = ((p.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
+    const size_t res_row = p.res ? static_cast<size_t>(p.res_mod > 0 ? row % p.res_mod : row) : 0;
+#pragma unroll
+    for (int cgrp = 0; cgrp < HALF / 32; ++cgrp) {
+      const int col0 = n0 + group * HALF + cgrp * 32;
+      if (col0 < p.Ncols) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = acc[cgrp * 32 + j];
+        float* yrow = p.y + static_cast<size_t>(row) * p.ldy + col0;
+        if (p.splits > 1) {
+          if (row_ok) {
+            if (vec_ok && col0 + 32 <= p.Ncols) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) red_add_v4(yrow + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.Ncols) atomicAdd(yrow + j, v[j]);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = col0 + j;
+            if (col < p.Ncols) {
+              float t = v[j];
+              if (p.scale) t *= __ldg(p.scale + col);
+              if (p.shift) t += __ldg(p.shift + col);
+              if (p.res && row_ok) t += __ldg(p.res + res_row * p.ldr + col);
+              v[j] = t;
+            } else {
+              v[j] = 0.f;
+            }
+          }
+          if (p.y_pre && row_ok) {
+            float* prow = p.y_pre + static_cast<size_t>(row) * p.ldy + col0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.Ncols) prow[j] = v[j];
+          }
+          if (p.act != ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act, p.slope);
+          }
+          if (row_ok) {
+            if (vec_ok && col0 + 32 <= p.Ncols) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(yrow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.Ncols) yrow[j] = v[j];
+            }
+          }
+          if (p.stats) {
+            float sq[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (!row_ok) v[j] = 0.f;
+              sq[j] = v[j] * v[j];
+            }
+            const float s1 = warp_transpose_reduce(v, lane);
+            const float s2 = warp_transpose_reduce(sq, lane);
+            if (col0 + lane < p.Ncols) {
+              float* st = p.stats + static_cast<size_t>(m_tile * 4 + q) * 2 * p.ldstat;
+              st[col0 + lane] = s1;
+              st[p.ldstat + col0 + lane] = s2;
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // ===================================================== MMA issuer (warp 8, one thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(BM, BN, MODE == MODE_WGRAD, MODE == MODE_WGRAD);
+      // K-major: 128B swizzle (type 2), LBO field 1, SBO = 1024 (8 rows x 128 B), k-step = +32 B inside the row.
+      // MN-major tf32: 128B swizzle with 32B base (type 1), LBO = 4096 (next 32-wide MN atom), SBO = 512 (next 4 k-rows),
+      // k-step = 8 k-rows = +1024 B.
+      constexpr uint32_t LAYOUT = (MODE == MODE_WGRAD) ? 1u : 2u;
+      constexpr uint32_t LBO = (MODE == MODE_WGRAD) ? 4096u : 16u;
+      constexpr uint32_t SBO = (MODE == MODE_WGRAD) ? 512u : 1024u;
+      constexpr uint32_t KSTEP = (MODE == MODE_WGRAD) ? 1024u : 32u;
+      for (int it = 0; it < nkb; ++it) {
+        const int s = it % Cfg::STAGES;
+        const int u = PROMOTE ? (it >> 1) : 0;
+        const int b = u & (NBUF - 1);
+        const bool unit_first = PROMOTE ? ((it & 1) == 0) : (it == 0);
+        const bool unit_last = PROMOTE ? ((it & 1) == 1 || it == nkb - 1) : (it == nkb - 1);
+        if (PROMOTE && unit_first) {
+          mbar_wait(&acce_bar[b], (((u / NBUF) & 1) ^ 1));
+          tc_fence_after();
+        }
+        mbar_wait(&full_bar[s], (it / Cfg::STAGES) & 1);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + static_cast<uint32_t>(b * BN);
+        const uint32_t stage = smem_base + s * Cfg::STAGE_BYTES;
+        const uint32_t a_hi = stage, a_lo = stage + Cfg::A_BYTES;
+        const uint32_t b_hi = stage + Cfg::A_BYTES * PREC, b_lo = b_hi + Cfg::B_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+          const uint32_t koff = kk * KSTEP;
+          const uint64_t da_hi = umma_desc(a_hi + koff, LBO, SBO, LAYOUT);
+          const uint64_t db_hi = umma_desc(b_hi + koff, LBO, SBO, LAYOUT);
+          mma_tf32_ss(tacc, da_hi, db_hi, idesc, !(unit_first && kk == 0));
+          if (PREC == 2) {
+            const uint64_t da_lo = umma_desc(a_lo + koff, LBO, SBO, LAYOUT);
+            const uint64_t db_lo = umma_desc(b_lo + koff, LBO, SBO, LAYOUT);
+            mma_tf32_ss(tacc, da_lo, db_hi, idesc, 1);
+            mma_tf32_ss(tacc, da_hi, db_lo, idesc, 1);
+          }
+        }
+        tc_commit(&empty_bar[s]);
+        if (unit_last) tc_commit(&accf_bar[b]);
+      }
+    }
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+}  // namespace cavp
