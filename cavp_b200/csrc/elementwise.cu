@@ -57,6 +57,14 @@ __global__ void add_inplace_kernel(float* __restrict__ dst, const float* __restr
     reinterpret_cast<float4*>(dst)[i] = a;
   }
 }
+__global__ void fill_strided_kernel(float* __restrict__ dst, int ld, long long rows, int C, float value) {
+  const long long total = rows * C;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / C;
+    dst[r * ld + (i - r * C)] = value;
+  }
+}
 // rows gathered: dst[i][:] = src[idx[i]][:]   (forward_audio feature shuffle, models/cavp_model.py:171-173)
 __global__ void gather_rows_kernel(const float* __restrict__ src, const long long* __restrict__ idx,
                                    float* __restrict__ dst, int nrows, int c, int accumulate_scatter) {
@@ -202,15 +210,23 @@ __global__ void colreduce_kernel(const float* __restrict__ dz, int lddz, const f
     *reinterpret_cast<float4*>(pp + ldp + c4 * 4) = s2;
   }
 }
-// out[k][c] = sum_i partials[i][k][c]  (k = 0..nk-1), fp64 accumulate
+// out[k][c] = sum_i partials[i][k][c]  (k = 0..nk-1), fp64 accumulate.  block = (32 channels, 32 part-lanes)
 __global__ void partials_sum_kernel(const float* __restrict__ partials, int nparts, int ldp, int C, int nk,
                                     float* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nk * C) return;
-  const int k = i / C, ch = i - k * C;
+  __shared__ double sh[32][33];
+  const int i = blockIdx.x * 32 + threadIdx.x;  // flat (k, channel)
   double s = 0.0;
-  for (int pidx = 0; pidx < nparts; ++pidx) s += partials[(static_cast<size_t>(pidx) * nk + k) * ldp + ch];
-  out[i] = static_cast<float>(s);
+  if (i < nk * C) {
+    const int k = i / C, ch = i - k * C;
+    for (int pidx = threadIdx.y; pidx < nparts; pidx += 32)
+      s += partials[(static_cast<size_t>(pidx) * nk + k) * ldp + ch];
+  }
+  sh[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && i < nk * C) {
+    for (int j = 1; j < 32; ++j) s += sh[j][threadIdx.x];
+    out[i] = static_cast<float>(s);
+  }
 }
 
 __global__ void bn_bwd_apply_kernel(const float* __restrict__ dz, int lddz, const float* __restrict__ z, int ldz,
@@ -484,6 +500,10 @@ using namespace cavp;
 extern "C" int cavp_zero(void* ptr, long long bytes, void* stream) {
   return static_cast<int>(cudaMemsetAsync(ptr, 0, static_cast<size_t>(bytes), ST(stream)));
 }
+extern "C" int cavp_fill_strided(float* dst, int ld, long long rows, int c, float value, void* stream) {
+  fill_strided_kernel<<<grid_for(rows * c, 256), 256, 0, ST(stream)>>>(dst, ld, rows, c, value);
+  CAVP_LAUNCH_CHECK();
+}
 extern "C" int cavp_nchw_to_nhwc(const float* src, float* dst, int n, int c, int hw, int cpad, void* stream) {
   nchw_to_nhwc_kernel<<<grid_for(static_cast<long long>(n) * hw, 256), 256, 0, ST(stream)>>>(src, dst, n, c, hw, cpad);
   CAVP_LAUNCH_CHECK();
@@ -541,7 +561,7 @@ extern "C" int cavp_colreduce(const float* dz, int lddz, const float* z, int ldz
   CAVP_LAUNCH_CHECK();
 }
 extern "C" int cavp_partials_sum(const float* partials, int nparts, int ldp, int C, int nk, float* out, void* stream) {
-  partials_sum_kernel<<<(nk * C + 127) / 128, 128, 0, ST(stream)>>>(partials, nparts, ldp, C, nk, out);
+  partials_sum_kernel<<<(nk * C + 31) / 32, dim3(32, 32), 0, ST(stream)>>>(partials, nparts, ldp, C, nk, out);
   CAVP_LAUNCH_CHECK();
 }
 extern "C" int cavp_bn_bwd_apply(const float* dz, int lddz, const float* z, int ldz, const float* y, int ldy,

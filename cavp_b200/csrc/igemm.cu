@@ -42,7 +42,8 @@ using namespace cavp;
 extern "C" int cavp_igemm(const float* x, const float* w, float* y, float* y_pre, const float* scale,
                           const float* shift, const float* res, float* stats, int nimg, int hs, int ws, int c, int ldx,
                           int ho, int wo, int r, int s, int stride, int pad, int dil, int dgrad, int ncols, int ldw,
-                          int ldy, int ldr, int res_mod, int ldstat, int act, float slope, int splits, int prec,
+                          int ldy, int ldr, int res_mod, int res_div, int ldstat, int act, float slope, int splits,
+                          int prec,
                           void* stream) {
   if (!x || !w || !y) return CAVP_ERR_NULL;
   if ((c & 3) || (ldx & 3) || (ldw & 3) || c <= 0 || ncols <= 0) return CAVP_ERR_ALIGN;
@@ -56,7 +57,7 @@ extern "C" int cavp_igemm(const float* x, const float* w, float* y, float* y_pre
   p.Nimg = nimg; p.Hs = hs; p.Ws = ws; p.C = c; p.ldx = ldx; p.Ho = ho; p.Wo = wo;
   p.R = r; p.S = s; p.stride = stride; p.pad = pad; p.dil = dil; p.dgrad = dgrad;
   p.M = static_cast<int>(M); p.Ncols = ncols; p.K = r * s * c; p.ldw = ldw; p.ldy = ldy; p.ldr = ldr;
-  p.res_mod = res_mod; p.ldstat = ldstat; p.act = act; p.slope = slope;
+  p.res_mod = res_mod; p.res_div = res_div; p.ldstat = ldstat; p.act = act; p.slope = slope;
   p.red_len = p.K;
   p.num_kb = (p.K + BK - 1) / BK;
   p.splits = splits < 1 ? 1 : (splits > p.num_kb ? p.num_kb : splits);

@@ -49,7 +49,7 @@ struct IgemmParams {
   int Ho, Wo;
   int R, S, stride, pad, dil;
   int dgrad;
-  int M, Ncols, K, ldw, ldy, ldr, res_mod, ldstat;
+  int M, Ncols, K, ldw, ldy, ldr, res_mod, res_div, ldstat;  // residual row = (row / res_div) % res_mod
   int red_len;  // length of the reduction dimension (K for MODE_ROW, P pixels for MODE_WGRAD)
   int act;
   float slope;
@@ -104,7 +104,7 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane)
 
 // ---------------------------------------------------------------------------------------------------------------
 template <int BN, int PREC, int MODE>
-__global__ void __launch_bounds__(CTA_THREADS, 1) igemm_kernel(const IgemmParams p) {
+__global__ void __maxnreg__(224) igemm_kernel(const IgemmParams p) {
   using Cfg = TileCfg<BN, PREC>;
   constexpr bool PROMOTE = Cfg::PROMOTE;
   constexpr int NBUF = Cfg::NBUF;
@@ -344,7 +344,12 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) igemm_kernel(const IgemmParams
     const int row = m0 + q * 32 + lane;
     const bool row_ok = row < p.M;
     const bool vec_ok = ((p.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
-    const size_t res_row = p.res ? static_cast<size_t>(p.res_mod > 0 ? row % p.res_mod : row) : 0;
+    size_t res_row = 0;
+    if (p.res) {
+      int rr_ = p.res_div > 1 ? row / p.res_div : row;
+      if (p.res_mod > 0) rr_ %= p.res_mod;
+      res_row = static_cast<size_t>(rr_);
+    }
 #pragma unroll
     for (int cgrp = 0; cgrp < HALF / 32; ++cgrp) {
       const int col0 = n0 + group * HALF + cgrp * 32;

@@ -1,0 +1,681 @@
+"""Host-side graph bookkeeping for the CAVP hot path.
+
+A `Graph` records, per forward op, a closure that computes the op's gradients; `backward()` replays them in reverse.
+Every arithmetic step is a C-ABI kernel from libcavp_b200.so (cavp_b200/_C.py); torch only owns device memory and
+streams.  Gradient fan-in is resolved inside kernels (igemm residual epilogue / in-place adds), never by torch ops.
+
+Activations are `Act`s: NHWC fp32 storage `[n*h*w, ld]` with a channel window `[off, off+c)`, so concat buffers and
+their slices need no copies.  Token tensors `[rows, N, C]` are the same thing with (h, w) = token grid.
+"""
+import torch
+
+from . import _C
+
+ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_GELU, ACT_SIGMOID = 0, 1, 2, 3, 4
+NUM_SMS = 148
+LEAKY_SLOPE = 0.01  # nn.LeakyReLU default (models/visual/deeplabv3/encoder_decoder.py:135)
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def pad4(c):
+    return (c + 3) // 4 * 4
+
+
+class Act:
+    """NHWC activation view: storage `buf` [n*h*w, ld] (contiguous rows), channels [off, off+c)."""
+
+    __slots__ = ("buf", "n", "h", "w", "c", "off", "grad", "parent", "needs_grad")
+
+    def __init__(self, buf, n, h, w, c, off=0, parent=None, needs_grad=True):
+        assert buf.dim() == 2 and buf.shape[0] == n * h * w, (tuple(buf.shape), n, h, w)
+        self.buf, self.n, self.h, self.w, self.c, self.off = buf, n, h, w, c, off
+        self.grad = None
+        self.parent = parent
+        self.needs_grad = needs_grad
+
+    @property
+    def ld(self):
+        return self.buf.stride(0)
+
+    @property
+    def rows(self):
+        return self.n * self.h * self.w
+
+    @property
+    def ptr(self):
+        return self.buf.data_ptr() + 4 * self.off
+
+    @property
+    def root(self):
+        return self if self.parent is None else self.parent
+
+    def slice(self, off, c):
+        return Act(self.buf, self.n, self.h, self.w, c, self.off + off, parent=self.root, needs_grad=self.needs_grad)
+
+    def dense(self):
+        """torch view [n, h, w, c] (no copy)."""
+        return self.buf[:, self.off:self.off + self.c].unflatten(0, (self.n, self.h, self.w))
+
+    def nchw(self):
+        """logical NCHW view with channels_last strides (no copy) - what the reference-facing API returns."""
+        return self.dense().permute(0, 3, 1, 2)
+
+
+def new_act(n, h, w, c, device, needs_grad=True):
+    return Act(torch.empty(n * h * w, c, device=device, dtype=torch.float32), n, h, w, c, needs_grad=needs_grad)
+
+
+class WeightRef:
+    """K-major [Cout_eff, K] operand of a Conv2d / Linear parameter plus the way its gradient goes back.
+
+    kinds: 'linear' [out, in]; 'cl' conv stored channels_last (zero-copy OHWI view); 'packed' conv with Cin % 4 != 0
+    (re-packed to pad4(Cin) every step); any kind may be row-padded to `pad_cout` (classifier: nc -> pad4(nc))."""
+
+    def __init__(self, g, param, pad_cout=None):
+        self.g, self.param = g, param
+        if param.dim() == 2:
+            self.kind, self.r, self.s = "linear", 1, 1
+            self.cout, self.cin = param.shape
+            wk = param.detach()
+            assert wk.is_contiguous()
+        else:
+            self.cout, ci, self.r, self.s = param.shape
+            if ci % 4 != 0:
+                self.kind, self.cin = "packed", pad4(ci)
+                wc = param.detach().contiguous()
+                wk = g.empty(self.cout, self.r * self.s * self.cin)
+                g.call("cavp_nchw_to_nhwc", wc.data_ptr(), wk.data_ptr(), self.cout, ci, self.r * self.s, self.cin)
+            else:
+                self.kind, self.cin = "cl", ci
+                v = param.detach().permute(0, 2, 3, 1)
+                assert v.is_contiguous(), "conv weights must be stored channels_last (cavp_b200.models converts them)"
+                wk = v.reshape(self.cout, self.r * self.s * ci)
+        self.K = self.r * self.s * self.cin
+        self.cout_eff = self.cout if pad_cout is None else pad_cout
+        if self.cout_eff != self.cout:
+            wp = g.zeros(self.cout_eff, self.K)
+            wp[:self.cout].copy_(wk)  # plumbing copy
+            wk = wp
+        self.wk = wk
+        self._wt = None
+
+    def transposed(self):
+        """[Cin][taps][Cout_eff] for the data-gradient GEMM."""
+        if self._wt is None:
+            taps = self.r * self.s
+            wt = self.g.empty(self.cin, taps * self.cout_eff)
+            self.g.call("cavp_transpose", self.wk.data_ptr(), wt.data_ptr(), self.cout_eff, self.cin, taps * self.cin,
+                        taps * self.cout_eff, taps, self.cin, self.cout_eff)
+            self._wt = wt
+        return self._wt
+
+    def deliver_grad(self, dwk):
+        """dwk: [Cout_eff, K] -> gradient with the parameter's shape / memory format."""
+        p, g = self.param, self.g
+        dwk = dwk[:self.cout]
+        if self.kind == "linear":
+            grad = dwk
+        elif self.kind == "cl":
+            grad = dwk.view(self.cout, self.r, self.s, self.cin).permute(0, 3, 1, 2)
+        else:
+            ci = p.shape[1]
+            grad = g.empty(self.cout, ci, self.r, self.s)
+            g.call("cavp_nhwc_to_nchw", dwk.data_ptr(), grad.data_ptr(), self.cout, ci, self.r * self.s, self.cin)
+        g.add_param_grad(p, grad)
+
+
+class Graph:
+    def __init__(self, device, prec=2, train=True, sync_bn_group=None):
+        self.device = device
+        self.prec = prec
+        self.train = train
+        self.tape = []
+        self.param_grads = {}  # id(param) -> gradient tensor
+        self.sync_bn_group = sync_bn_group
+        self._const = {}
+        self.launches = 0
+        self.profile = None  # set to [] to record (name, start_event, end_event, flops, bytes) per kernel launch
+        self._work = (0.0, 0.0)
+
+    # ------------------------------------------------------------------ small helpers
+    def call(self, name, *args):
+        self.launches += 1
+        if self.profile is None:
+            _C.call(name, *args, _stream())
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _C.call(name, *args, _stream())
+        e1.record()
+        self.profile.append((name, e0, e1) + self._work)
+        self._work = (0.0, 0.0)
+
+    def work(self, flops=0.0, nbytes=0.0):
+        """algorithmic work of the NEXT kernel launch (only used when profiling)."""
+        if self.profile is not None:
+            self._work = (float(flops), float(nbytes))
+
+    def empty(self, *shape, dtype=torch.float32):
+        return torch.empty(*shape, device=self.device, dtype=dtype)
+
+    def zeros(self, *shape, dtype=torch.float32):
+        t = torch.empty(*shape, device=self.device, dtype=dtype)
+        self.call("cavp_zero", t.data_ptr(), t.numel() * t.element_size())
+        return t
+
+    def const_vec(self, n, value):
+        key = (n, value)
+        if key not in self._const:
+            self._const[key] = torch.full((n,), float(value), device=self.device)
+        return self._const[key]
+
+    def zero_act(self, a):
+        if a.off == 0 and a.c == a.ld:
+            self.call("cavp_zero", a.buf.data_ptr(), a.rows * a.ld * 4)
+        else:
+            self.call("cavp_fill_strided", a.ptr, a.ld, a.rows, a.c, 0.0)
+
+    def copy_act(self, dst, src):
+        self.call("cavp_bn_apply", src.ptr, src.ld, self.const_vec(src.c, 1).data_ptr(),
+                  self.const_vec(src.c, 0).data_ptr(), 0, 0, dst.ptr, dst.ld, src.rows, src.c, ACT_NONE, 0.0)
+
+    def add_act(self, dst, src):
+        """dst += src"""
+        self.call("cavp_bn_apply", src.ptr, src.ld, self.const_vec(src.c, 1).data_ptr(),
+                  self.const_vec(src.c, 0).data_ptr(), dst.ptr, dst.ld, dst.ptr, dst.ld, src.rows, src.c, ACT_NONE, 0.0)
+
+    def grad_of(self, a):
+        """Gradient Act of `a` (None if nobody produced one)."""
+        root = a.root
+        if root.grad is None:
+            return None
+        g = root.grad
+        if a is root:
+            return g
+        return Act(g.buf, a.n, a.h, a.w, a.c, a.off - root.off + g.off)
+
+    def grad_target(self, a):
+        """-> (gradient Act, accumulate?)  allocating the gradient buffer on first use."""
+        root = a.root
+        fresh = root.grad is None
+        if fresh:
+            root.grad = Act(torch.empty(root.rows, root.ld, device=self.device), root.n, root.h, root.w, root.c, root.off)
+            if a is not root and a.c != root.c:  # a partial writer comes first: start the whole buffer from zero
+                self.call("cavp_zero", root.grad.buf.data_ptr(), root.grad.buf.numel() * 4)
+                fresh = False
+        return self.grad_of(a), (not fresh)
+
+    def add_param_grad(self, p, g):
+        key = id(p)
+        if key in self.param_grads:
+            old = self.param_grads[key]
+            if not (old.is_contiguous() and g.is_contiguous()):
+                old = old.contiguous(memory_format=torch.channels_last) if old.dim() == 4 else old.contiguous()
+                g = g.contiguous(memory_format=torch.channels_last) if g.dim() == 4 else g.contiguous()
+                self.param_grads[key] = old
+            self.call("cavp_add_inplace", old.data_ptr(), g.data_ptr(), g.numel(), 1.0)
+        else:
+            self.param_grads[key] = g
+
+    def accumulate_grad(self, a, g, res_mod=0, res_div=0):
+        """a.grad += g where g has the row layout of a consumer that read `a` through an igemm residual epilogue:
+        consumer row r reads a-row (r / res_div) % res_mod."""
+        da, accumulate = self.grad_target(a)
+        if res_div > 1:  # broadcast over the pixels of an image: sum over pixels
+            assert res_mod == 0
+            tmp = da if (not accumulate and da.ld == da.c) else new_act(a.n, a.h, a.w, a.c, self.device)
+            self.call("cavp_pixel_sum", g.ptr, g.ld, tmp.ptr, a.rows, res_div, a.c, 1.0)
+            if tmp is not da:
+                (self.add_act if accumulate else self.copy_act)(da, tmp)
+            return
+        reps = 1 if res_mod == 0 else g.rows // res_mod
+        nrows = g.rows // reps
+        for i in range(reps):
+            part = Act(g.buf[i * nrows:(i + 1) * nrows], a.n, a.h, a.w, a.c, g.off)
+            if i == 0 and not accumulate:
+                self.copy_act(da, part)
+            else:
+                self.add_act(da, part)
+
+    # ------------------------------------------------------------------ igemm wrappers
+    def _igemm(self, x, wk, ncols, ldw, y, *, geom, src_hw=None, dgrad=0, y_pre=None, scale=None, shift=None, res=None,
+               res_mod=0, res_div=0, stats_ptr=0, ldstat=0, act=ACT_NONE, splits=1):
+        """geom = (ho, wo, r, s, stride, pad, dil).  x: A-operand source Act; y: output Act (rows = x.n*ho*wo)."""
+        ho, wo, r, s, stride, pad, dil = geom
+        hs, ws = (x.h, x.w) if src_hw is None else src_hw
+        self.work(flops=2.0 * x.n * ho * wo * ncols * r * s * x.c)
+        self.call("cavp_igemm", x.ptr, wk.data_ptr(), y.ptr, 0 if y_pre is None else y_pre.ptr, _C.ptr(scale),
+                  _C.ptr(shift), 0 if res is None else res.ptr, stats_ptr, x.n, hs, ws, x.c, x.ld, ho, wo, r, s, stride,
+                  pad, dil, dgrad, ncols, ldw, y.ld, 0 if res is None else res.ld, res_mod, res_div, ldstat, act,
+                  LEAKY_SLOPE, splits, self.prec)
+
+    @staticmethod
+    def fwd_splits(M, ncols, K):
+        bn = 128 if ncols > 64 else 64
+        tiles = ((M + 127) // 128) * ((ncols + bn - 1) // bn)
+        num_kb = (K + 31) // 32
+        if tiles >= 96 or num_kb < 16:
+            return 1
+        return max(1, min(num_kb // 8, (NUM_SMS + tiles - 1) // tiles))
+
+    @staticmethod
+    def wgrad_splits(P, cout, K):
+        bn = 128 if K > 64 else 64
+        tiles = ((cout + 127) // 128) * ((K + bn - 1) // bn)
+        num_kb = (P + 31) // 32
+        return max(1, min(num_kb // 4, (2 * NUM_SMS + tiles - 1) // tiles))
+
+    @staticmethod
+    def colreduce_blocks(M, C):
+        return max(1, min((M + 31) // 32, 4 * NUM_SMS // max(1, (C // 4 + 63) // 64)))
+
+    def stats_from_tensor(self, y, stats):
+        """BN statistics partials (sum, sum of squares) of an already materialised tensor (split-K path)."""
+        stats_t, stats_ptr, nparts, ldstat = stats
+        window = Act(stats_t.view(nparts * 2, ldstat), 1, 1, nparts * 2, y.c, (stats_ptr - stats_t.data_ptr()) // 4)
+        self.zero_act(window)
+        nblk = min(nparts, self.colreduce_blocks(y.rows, y.c))
+        self.call("cavp_colreduce", y.ptr, y.ld, 0, 0, y.ptr, y.ld, self.const_vec(y.c, 0).data_ptr(),
+                  self.const_vec(y.c, 1).data_ptr(), y.rows, y.c, ACT_NONE, 0.0, 0, 0, stats_ptr, ldstat, nblk)
+
+    # ------------------------------------------------------------------ conv / linear
+    def conv(self, x, w, *, stride=1, pad=0, dil=1, bias=None, act=ACT_NONE, want_stats=False, out=None, res=None,
+             res_mod=0, res_div=0, save_pre=False, stats_buf=None, pad_cout=None, name=""):
+        """y = act(conv(x, w) + bias + res)  (Linear = 1x1 conv over tokens).  `w`, `bias` are nn.Parameters.
+        want_stats: also produce the BatchNorm sum / sum-of-squares partials of y.  Returns (y, stats)."""
+        wr = w if isinstance(w, WeightRef) else WeightRef(self, w, pad_cout)
+        co, r, s, K = wr.cout_eff, wr.r, wr.s, wr.K
+        assert wr.cin == x.c, (name, wr.cin, x.c)
+        bias_t = None
+        if bias is not None:
+            bias_t = bias.detach()
+            if co != wr.cout:
+                bp = self.zeros(co)
+                bp[:wr.cout].copy_(bias_t)
+                bias_t = bp
+        ho = (x.h + 2 * pad - dil * (r - 1) - 1) // stride + 1
+        wo = (x.w + 2 * pad - dil * (s - 1) - 1) // stride + 1
+        y = out if out is not None else new_act(x.n, ho, wo, co, self.device)
+        assert y.rows == x.n * ho * wo and y.c == co, (name, y.rows, x.n, ho, wo, y.c, co)
+        M = y.rows
+        geom = (ho, wo, r, s, stride, pad, dil)
+        pre = new_act(x.n, ho, wo, co, self.device) if save_pre else None
+        stats = None
+        if want_stats:
+            nparts = ((M + 127) // 128) * 4
+            if stats_buf is None:
+                stats_t = self.empty(nparts, 2, co)
+                stats = (stats_t, stats_t.data_ptr(), nparts, co)
+            else:
+                stats = stats_buf  # (tensor [nparts, 2, ldstat], pointer offset to our columns, nparts, ldstat)
+                assert stats[2] == nparts
+        splits = self.fwd_splits(M, co, K)
+        if splits > 1 and (save_pre or res_mod or res_div):
+            splits = 1
+        if splits > 1:
+            simple = bias_t is None and act == ACT_NONE and res is None
+            raw = y if simple else new_act(x.n, ho, wo, co, self.device)
+            self.zero_act(raw)
+            self._igemm(x, wr.wk, co, K, raw, geom=geom, splits=splits)
+            if not simple:
+                self.call("cavp_bn_apply", raw.ptr, raw.ld, self.const_vec(co, 1).data_ptr(),
+                          (bias_t if bias_t is not None else self.const_vec(co, 0)).data_ptr(),
+                          0 if res is None else res.ptr, 0 if res is None else res.ld, y.ptr, y.ld, M, co, act,
+                          LEAKY_SLOPE)
+            if want_stats:
+                self.stats_from_tensor(y, stats)
+        else:
+            self._igemm(x, wr.wk, co, K, y, geom=geom, y_pre=pre, shift=bias_t, res=res, res_mod=res_mod,
+                        res_div=res_div, stats_ptr=0 if stats is None else stats[1],
+                        ldstat=0 if stats is None else stats[3], act=act)
+
+        if self.train:
+            def bwd():
+                dy = self.grad_of(y)
+                if dy is None:
+                    return
+                g = dy
+                if act != ACT_NONE or bias is not None:
+                    # g = dy * act'(.) and the bias gradient (column sums of g) from one pass
+                    zin, gout = None, None
+                    if act == ACT_GELU:
+                        assert dy.ld == dy.c and pre is not None
+                        g = new_act(y.n, y.h, y.w, co, self.device)
+                        self.call("cavp_gelu_bwd", dy.ptr, pre.ptr, g.ptr, M * co)
+                    elif act in (ACT_RELU, ACT_LEAKY):
+                        zin = y
+                        gout = new_act(y.n, y.h, y.w, co, self.device)
+                    elif act != ACT_NONE:
+                        raise _C.CavpError("unsupported fused activation in backward")
+                    if zin is not None or bias is not None:
+                        nblk = self.colreduce_blocks(M, co)
+                        partials = self.empty(nblk, 2, co)
+                        self.call("cavp_colreduce", g.ptr, g.ld, 0 if zin is None else zin.ptr,
+                                  0 if zin is None else zin.ld, 0, 0, 0, 0, M, co, act if zin is not None else ACT_NONE,
+                                  LEAKY_SLOPE, 0 if gout is None else gout.ptr, 0 if gout is None else gout.ld,
+                                  partials.data_ptr(), co, nblk)
+                        if gout is not None:
+                            g = gout
+                        if bias is not None and bias.requires_grad:
+                            sums = self.empty(2, co)
+                            self.call("cavp_partials_sum", partials.data_ptr(), nblk, co, co, 2, sums.data_ptr())
+                            self.add_param_grad(bias, sums[0, :wr.cout])
+                if res is not None and res.needs_grad:
+                    self.accumulate_grad(res, g, res_mod, res_div)
+                if wr.param.requires_grad:
+                    dwk = self.empty(co, K)
+                    wsplits = self.wgrad_splits(M, co, K)
+                    if wsplits > 1:
+                        self.call("cavp_zero", dwk.data_ptr(), dwk.numel() * 4)
+                    self.work(flops=2.0 * M * co * K)
+                    self.call("cavp_igemm_wgrad", g.ptr, x.ptr, dwk.data_ptr(), x.n, x.h, x.w, x.c, x.ld, ho, wo, r, s,
+                              stride, pad, dil, co, g.ld, wsplits, self.prec)
+                    wr.deliver_grad(dwk)
+                if x.needs_grad:
+                    wt = wr.transposed()
+                    dx, accumulate = self.grad_target(x)
+                    dsplits = self.fwd_splits(x.rows, wr.cin, r * s * co)
+                    gs = Act(g.buf, y.n, ho, wo, co, g.off)
+                    dgeom = (x.h, x.w, r, s, stride, pad, dil)
+                    if dsplits > 1:
+                        if not accumulate:
+                            self.zero_act(dx)
+                        self._igemm(gs, wt, wr.cin, r * s * co, dx, geom=dgeom, dgrad=1, splits=dsplits)
+                    else:
+                        self._igemm(gs, wt, wr.cin, r * s * co, dx, geom=dgeom, dgrad=1, res=dx if accumulate else None)
+            self.tape.append(bwd)
+        return y, stats
+
+    # ------------------------------------------------------------------ BatchNorm (+ activation, + residual)
+    def bn_act(self, y, stats, bn, *, act=ACT_RELU, res=None, out=None):
+        """z = act(BN(y) + res) with batch statistics taken from the igemm epilogue partials (train mode)."""
+        C = y.c
+        z = out if out is not None else new_act(y.n, y.h, y.w, C, self.device)
+        coeffs = self.empty(4, C)  # mean, invstd, scale, shift
+        stats_t, stats_ptr, nparts, ldstat = stats
+        count = float(y.rows)
+        momentum = bn.momentum if bn.momentum is not None else 0.1
+        sync = self.sync_bn_group is not None and isinstance(bn, torch.nn.SyncBatchNorm)
+        head = (stats_ptr, nparts, ldstat, C)
+        tail = (bn.weight.data_ptr(), bn.bias.data_ptr(), bn.running_mean.data_ptr(), bn.running_var.data_ptr(),
+                momentum, bn.eps, coeffs[0].data_ptr(), coeffs[1].data_ptr(), coeffs[2].data_ptr(),
+                coeffs[3].data_ptr())
+        if sync:
+            import torch.distributed as dist
+            sums = self.empty(2 * C + 1, dtype=torch.float64)
+            self.call("cavp_bn_finalize", *head, count, *tail, sums.data_ptr(), 1)
+            sums[2 * C] = count
+            dist.all_reduce(sums, group=self.sync_bn_group)
+            count = float(sums[2 * C].item())
+            self.call("cavp_bn_finalize", *head, count, *tail, sums.data_ptr(), 2)
+        else:
+            self.call("cavp_bn_finalize", *head, count, *tail, 0, 0)
+        bn.num_batches_tracked += 1
+        self.call("cavp_bn_apply", y.ptr, y.ld, coeffs[2].data_ptr(), coeffs[3].data_ptr(),
+                  0 if res is None else res.ptr, 0 if res is None else res.ld, z.ptr, z.ld, y.rows, C, act, LEAKY_SLOPE)
+
+        def bwd():
+            dz = self.grad_of(z)
+            if dz is None:
+                return
+            M = y.rows
+            nblk = self.colreduce_blocks(M, C)
+            partials = self.empty(nblk, 2, C)
+            zin = z if act != ACT_NONE else None
+            self.call("cavp_colreduce", dz.ptr, dz.ld, 0 if zin is None else zin.ptr, 0 if zin is None else zin.ld,
+                      y.ptr, y.ld, coeffs[0].data_ptr(), coeffs[1].data_ptr(), M, C, act, LEAKY_SLOPE, 0, 0,
+                      partials.data_ptr(), C, nblk)
+            sums = self.empty(2, C)
+            self.call("cavp_partials_sum", partials.data_ptr(), nblk, C, C, 2, sums.data_ptr())
+            local = sums
+            if sync:
+                import torch.distributed as dist
+                local = sums.clone()
+                dist.all_reduce(sums, group=self.sync_bn_group)
+            self.add_param_grad(bn.bias, local[0])
+            self.add_param_grad(bn.weight, local[1])
+            dy, acc_y = self.grad_target(y)
+            assert not acc_y, "a BatchNorm input has exactly one consumer"
+            dres, tmp = None, None
+            if res is not None and res.needs_grad:
+                dres, acc_r = self.grad_target(res)
+                if acc_r:
+                    tmp = new_act(res.n, res.h, res.w, res.c, self.device)
+            tgt = tmp if tmp is not None else dres
+            self.call("cavp_bn_bwd_apply", dz.ptr, dz.ld, 0 if zin is None else zin.ptr, 0 if zin is None else zin.ld,
+                      y.ptr, y.ld, coeffs[0].data_ptr(), coeffs[1].data_ptr(), bn.weight.data_ptr(), sums.data_ptr(),
+                      1.0 / count, M, C, act, LEAKY_SLOPE, dy.ptr, dy.ld, 0 if tgt is None else tgt.ptr,
+                      0 if tgt is None else tgt.ld)
+            if tmp is not None:
+                self.add_act(dres, tmp)
+        self.tape.append(bwd)
+        return z
+
+    def conv_bn(self, x, conv_w, bn, *, stride=1, pad=0, dil=1, act=ACT_RELU, res=None, out=None, name=""):
+        """conv -> BN -> (+res) -> act.  Eval mode folds BN, residual and activation into the igemm epilogue."""
+        if not self.train:
+            wr = WeightRef(self, conv_w)
+            co, r, s = wr.cout_eff, wr.r, wr.s
+            coeffs = self.empty(2, co)
+            self.call("cavp_bn_eval_coeffs", bn.weight.data_ptr(), bn.bias.data_ptr(), bn.running_mean.data_ptr(),
+                      bn.running_var.data_ptr(), bn.eps, co, coeffs[0].data_ptr(), coeffs[1].data_ptr())
+            ho = (x.h + 2 * pad - dil * (r - 1) - 1) // stride + 1
+            wo = (x.w + 2 * pad - dil * (s - 1) - 1) // stride + 1
+            y = out if out is not None else new_act(x.n, ho, wo, co, self.device)
+            splits = self.fwd_splits(y.rows, co, wr.K)
+            if splits > 1:
+                raw = new_act(x.n, ho, wo, co, self.device)
+                self.zero_act(raw)
+                self._igemm(x, wr.wk, co, wr.K, raw, geom=(ho, wo, r, s, stride, pad, dil), splits=splits)
+                self.call("cavp_bn_apply", raw.ptr, raw.ld, coeffs[0].data_ptr(), coeffs[1].data_ptr(),
+                          0 if res is None else res.ptr, 0 if res is None else res.ld, y.ptr, y.ld, y.rows, co, act,
+                          LEAKY_SLOPE)
+            else:
+                self._igemm(x, wr.wk, co, wr.K, y, geom=(ho, wo, r, s, stride, pad, dil), scale=coeffs[0],
+                            shift=coeffs[1], res=res, act=act)
+            return y
+        y, stats = self.conv(x, conv_w, stride=stride, pad=pad, dil=dil, want_stats=True, name=name)
+        return self.bn_act(y, stats, bn, act=act, res=res, out=out)
+
+    def bn_eval(self, y, bn, *, act=ACT_RELU, out=None):
+        """eval-mode BN (+act) of an already materialised tensor (ASPP map_bn over the concat)."""
+        C = y.c
+        z = out if out is not None else new_act(y.n, y.h, y.w, C, self.device)
+        coeffs = self.empty(2, C)
+        self.call("cavp_bn_eval_coeffs", bn.weight.data_ptr(), bn.bias.data_ptr(), bn.running_mean.data_ptr(),
+                  bn.running_var.data_ptr(), bn.eps, C, coeffs[0].data_ptr(), coeffs[1].data_ptr())
+        self.call("cavp_bn_apply", y.ptr, y.ld, coeffs[0].data_ptr(), coeffs[1].data_ptr(), 0, 0, z.ptr, z.ld, y.rows, C,
+                  act, LEAKY_SLOPE)
+        return z
+
+    # ------------------------------------------------------------------ pooling / resampling / views
+    def maxpool(self, x, k, stride, pad):
+        ho = (x.h + 2 * pad - k) // stride + 1
+        wo = (x.w + 2 * pad - k) // stride + 1
+        y = new_act(x.n, ho, wo, x.c, self.device)
+        idx = self.empty(y.rows, x.c, dtype=torch.int32) if self.train else None
+        self.call("cavp_maxpool_fwd", x.ptr, x.ld, y.ptr, y.ld, _C.ptr(idx), x.n, x.h, x.w, x.c, k, stride, pad, ho, wo)
+        if self.train:
+            def bwd():
+                dy = self.grad_of(y)
+                if dy is None or not x.needs_grad:
+                    return
+                dx, accumulate = self.grad_target(x)
+                if not accumulate:
+                    self.zero_act(dx)
+                self.call("cavp_maxpool_bwd", dy.ptr, dy.ld, idx.data_ptr(), dx.ptr, dx.ld, y.rows, x.c)
+            self.tape.append(bwd)
+        return y
+
+    def global_avgpool(self, x):
+        y = new_act(x.n, 1, 1, x.c, self.device)
+        hw = x.h * x.w
+        self.call("cavp_pixel_sum", x.ptr, x.ld, y.ptr, x.n, hw, x.c, 1.0 / hw)
+        if self.train:
+            def bwd():
+                dy = self.grad_of(y)
+                if dy is None or not x.needs_grad:
+                    return
+                dx, accumulate = self.grad_target(x)
+                self.call("cavp_pixel_bcast", dy.ptr, dx.ptr, dx.ld, x.n, hw, x.c, 1.0 / hw, 1 if accumulate else 0)
+            self.tape.append(bwd)
+        return y
+
+    def global_maxpool(self, x):
+        y = new_act(x.n, 1, 1, x.c, self.device)
+        hw = x.h * x.w
+        arg = self.empty(x.n, x.c, dtype=torch.int32)
+        self.call("cavp_pixel_max", x.ptr, x.ld, y.ptr, arg.data_ptr(), x.n, hw, x.c)
+        if self.train:
+            def bwd():
+                dy = self.grad_of(y)
+                if dy is None or not x.needs_grad:
+                    return
+                dx, accumulate = self.grad_target(x)
+                assert not accumulate
+                self.zero_act(dx)
+                self.call("cavp_pixel_max_bwd", dy.ptr, arg.data_ptr(), dx.ptr, dx.ld, x.n, hw, x.c)
+            self.tape.append(bwd)
+        return y
+
+    def bilinear(self, x, hout, wout, align_corners, out=None):
+        y = out if out is not None else new_act(x.n, hout, wout, x.c, self.device)
+        self.call("cavp_bilinear_fwd", x.ptr, x.ld, x.h, x.w, y.ptr, y.ld, hout, wout, x.n, x.c, int(align_corners), 0)
+        if self.train:
+            def bwd():
+                dy = self.grad_of(y)
+                if dy is None or not x.needs_grad:
+                    return
+                dx, accumulate = self.grad_target(x)
+                tgt = dx if not accumulate else new_act(x.n, x.h, x.w, x.c, self.device)
+                self.call("cavp_bilinear_bwd", dy.ptr, dy.ld, hout, wout, tgt.ptr, tgt.ld, x.h, x.w, x.n, x.c,
+                          int(align_corners), 0, x.n)
+                if accumulate:
+                    self.add_act(dx, tgt)
+            self.tape.append(bwd)
+        return y
+
+    def flatten(self, x):
+        """[n, h, w, c] -> [n, 1, 1, h*w*c] (NHWC flatten of models/audio/backbones/vgg.py:19-22); no copy."""
+        assert x.off == 0 and x.ld == x.c and x.parent is None
+        f = Act(x.buf.view(x.n, x.h * x.w * x.c), x.n, 1, 1, x.h * x.w * x.c, needs_grad=x.needs_grad)
+        if self.train:
+            def bwd():
+                df = self.grad_of(f)
+                if df is None:
+                    return
+                assert x.grad is None
+                x.grad = Act(df.buf.view(x.rows, x.c), x.n, x.h, x.w, x.c)
+            self.tape.append(bwd)
+        return f
+
+    def upsample_to_nchw(self, x, nc, hout, wout):
+        """Final prediction: bilinear (align_corners=False) of the first `nc` channels -> torch NCHW tensor."""
+        pred = self.empty(x.n, nc, hout, wout)
+        self.call("cavp_bilinear_fwd", x.ptr, x.ld, x.h, x.w, pred.data_ptr(), 0, hout, wout, x.n, nc, 0, 1)
+        return pred
+
+    def upsample_to_nchw_backward(self, x, nc, dpred, n_valid=None):
+        """Seed x.grad from the gradient of the full-resolution prediction (NCHW, contiguous)."""
+        assert dpred.is_contiguous()
+        dx, accumulate = self.grad_target(x)
+        assert not accumulate
+        if x.c != nc:
+            self.zero_act(dx)
+        hout, wout = dpred.shape[-2:]
+        self.call("cavp_bilinear_bwd", dpred.data_ptr(), 0, hout, wout, dx.ptr, dx.ld, x.h, x.w, x.n, nc, 0, 1,
+                  x.n if n_valid is None else n_valid)
+
+    # ------------------------------------------------------------------ fusion ops
+    def layernorm(self, x, ln):
+        assert x.ld == x.c and x.off == 0
+        y = new_act(x.n, x.h, x.w, x.c, self.device)
+        T = x.rows
+        mr = self.empty(2, T)
+        self.call("cavp_layernorm_fwd", x.ptr, ln.weight.data_ptr(), ln.bias.data_ptr(), y.ptr, mr[0].data_ptr(),
+                  mr[1].data_ptr(), T, x.c, ln.eps)
+        if self.train:
+            def bwd():
+                dy = self.grad_of(y)
+                if dy is None:
+                    return
+                assert dy.ld == dy.c
+                nparts = _C.query("cavp_layernorm_bwd_nparts", T)
+                partials = self.empty(nparts, 2, x.c)
+                dx, accumulate = self.grad_target(x)
+                self.call("cavp_layernorm_bwd", dy.ptr, x.ptr, ln.weight.data_ptr(), mr[0].data_ptr(), mr[1].data_ptr(),
+                          dx.ptr if accumulate else 0, dx.ptr, partials.data_ptr(), T, x.c)
+                sums = self.empty(2, x.c)
+                self.call("cavp_partials_sum", partials.data_ptr(), nparts, x.c, x.c, 2, sums.data_ptr())
+                self.add_param_grad(ln.weight, sums[0])
+                self.add_param_grad(ln.bias, sums[1])
+            self.tape.append(bwd)
+        return y
+
+    def gate(self, q, k, v, heads=4):
+        """models/attn.py:73-106 with one key/value token per row.  q [Bq, N, C] (Act n = Bq), k / v [rows, C]."""
+        Bq, N, C = q.n, q.h * q.w, q.c
+        rows = k.rows
+        rep = rows // Bq
+        assert rep * Bq == rows and q.ld == C and k.ld == C and v.ld == C
+        x = new_act(rows, q.h, q.w, C, self.device)
+        attn = self.empty(rows, heads, N)
+        self.work(nbytes=4.0 * (Bq * N * C + rows * N * C + rows * heads * N + 2 * rows * C))
+        self.call("cavp_gate_fwd", q.ptr, k.ptr, v.ptr, x.ptr, attn.data_ptr(), Bq, rep, N, C, heads)
+        if self.train:
+            def bwd():
+                dx = self.grad_of(x)
+                if dx is None:
+                    return
+                dq, acc_q = self.grad_target(q)
+                dk, acc_k = self.grad_target(k)
+                dv, acc_v = self.grad_target(v)
+                assert not (acc_q or acc_k or acc_v) and dx.ld == C
+                self.zero_act(dk)
+                self.zero_act(dv)
+                self.work(nbytes=4.0 * (rows * N * C + 2 * Bq * N * C + rows * heads * N + 4 * rows * C))
+                self.call("cavp_gate_bwd", dx.ptr, q.ptr, k.ptr, v.ptr, attn.data_ptr(), dq.ptr, dk.ptr, dv.ptr, Bq, rep,
+                          N, C, heads)
+            self.tape.append(bwd)
+        return x, attn
+
+    def gather_rows(self, x, idx):
+        """y = x[idx] over rows (feature-level audio shuffle, models/cavp_model.py:171)."""
+        assert x.ld == x.c
+        y = new_act(idx.numel(), 1, 1, x.c, self.device)
+        self.call("cavp_gather_rows", x.ptr, idx.data_ptr(), y.ptr, idx.numel(), x.c, 0)
+        if self.train:
+            def bwd():
+                dy = self.grad_of(y)
+                if dy is None:
+                    return
+                dx, accumulate = self.grad_target(x)
+                if not accumulate:
+                    self.zero_act(dx)
+                self.call("cavp_gather_rows", dy.ptr, idx.data_ptr(), dx.ptr, idx.numel(), x.c, 1)
+            self.tape.append(bwd)
+        return y
+
+    def concat_rows(self, a, b):
+        """row-wise concatenation (torch.cat(dim=0)) of two [rows, C] Acts."""
+        y = new_act(a.rows + b.rows, 1, 1, a.c, self.device)
+        self.copy_act(Act(y.buf[:a.rows], a.rows, 1, 1, a.c), a)
+        self.copy_act(Act(y.buf[a.rows:], b.rows, 1, 1, b.c), b)
+        if self.train:
+            def bwd():
+                dy = self.grad_of(y)
+                if dy is None:
+                    return
+                self.accumulate_grad(a, Act(dy.buf[:a.rows], a.n, a.h, a.w, a.c))
+                self.accumulate_grad(b, Act(dy.buf[a.rows:], b.n, b.h, b.w, b.c))
+            self.tape.append(bwd)
+        return y
+
+    # ------------------------------------------------------------------ backward driver
+    def backward(self):
+        for fn in reversed(self.tape):
+            fn()
+        self.tape = []

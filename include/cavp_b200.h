@@ -1,18 +1,145 @@
+/* cavp_b200 - C ABI of the B200 (sm_100a) kernels behind the CAVP hot path.
+ *
+ * The reference (cyh-0/CAVP) is pure Python/PyTorch: it has no FFI of its own.  Each entry point below replaces the
+ * torch op(s) that the reference calls at the cited file:line (paths relative to the reference repo), and is what a
+ * ctypes binding on the reference side would bind.  Conventions:
+ *   - raw device pointers, explicit shapes / leading dimensions, `void* stream` = cudaStream_t, int status return
+ *     (0 = ok, <0 = argument error below, >0 = cudaError_t); nothing throws across the ABI;
+ *   - the caller owns every buffer (outputs, workspaces); kernels keep no global state;
+ *   - activations are NHWC fp32 with a pixel stride `ld` (>= channels, multiple of 4), so a channel slice of a concat
+ *     buffer is an ordinary operand; weights are [Cout][R][S][Cin] (torch channels_last storage of an OIHW tensor);
+ *   - `prec`: 1 = TF32 products, 2 = 3xTF32 products + fp32 register promotion (fp32-parity mode).
+ */
 #pragma once
 #ifdef __cplusplus
 extern "C" {
 #endif
+
 #define CAVP_OK 0
 #define CAVP_ERR_NULL (-1)
 #define CAVP_ERR_ALIGN (-2)
 #define CAVP_ERR_ARG (-3)
+
+/* activation codes for `act` */
+#define CAVP_ACT_NONE 0
+#define CAVP_ACT_RELU 1
+#define CAVP_ACT_LEAKY 2
+#define CAVP_ACT_GELU 3
+#define CAVP_ACT_SIGMOID 4
+
+/* ---- tensor-core tiles (csrc/igemm.cu) ---------------------------------------------------------------------------
+ * cavp_igemm: y[M][ldy] = epilogue( im2col(x)[M][K] * w[ncols][K]^T ),  M = nimg*ho*wo, K = r*s*c.
+ *   Replaces F.conv2d / nn.Conv2d.forward (models/visual/backbones/resnet.py:75-98,107-121;
+ *   models/visual/deeplabv3/encoder_decoder.py:62-75,84-88,137-156; models/audio/backbones/vgg.py:26-36) and
+ *   F.linear / nn.Linear (models/attn.py:30-39,64-71,100-104; timm Mlp; vgg.py:11-16) with r=s=1.
+ *   dgrad=1 runs the transposed-stride gather (x = dY, w = weights transposed to [Cin][R][S][Cout], rows = input pixels):
+ *   the data gradient of the same convolution (autograd's convolution_backward, trainer_cavp_vpo_mono.py:191).
+ *   epilogue: v = acc*scale[col] + shift[col] + res[(row/res_div)%res_mod][col]; y_pre = v; y = act(v);
+ *   stats (optional) receives per-(row-tile, warp) column sums of y and y^2: [ceil(M/128)*4][2][ldstat] - the
+ *   BatchNorm batch statistics (train mode) without a second pass over y.
+ *   splits > 1 splits K over CTAs and accumulates raw products into a PRE-ZEROED y with red.global (no epilogue). */
 int cavp_igemm(const float* x, const float* w, float* y, float* y_pre, const float* scale, const float* shift,
                const float* res, float* stats, int nimg, int hs, int ws, int c, int ldx, int ho, int wo, int r, int s,
-               int stride, int pad, int dil, int dgrad, int ncols, int ldw, int ldy, int ldr, int res_mod, int ldstat,
-               int act, float slope, int splits, int prec, void* stream);
+               int stride, int pad, int dil, int dgrad, int ncols, int ldw, int ldy, int ldr, int res_mod, int res_div,
+               int ldstat, int act, float slope, int splits, int prec, void* stream);
+/* cavp_igemm_wgrad: dw[cout][r*s*c] (+)= dy[P][cout]^T * im2col(x)[P][r*s*c]   (weight gradient; P = nimg*ho*wo).
+ *   splits > 1 accumulates into a PRE-ZEROED dw. */
 int cavp_igemm_wgrad(const float* dy, const float* x, float* dw, int nimg, int hs, int ws, int c, int ldx, int ho,
                      int wo, int r, int s, int stride, int pad, int dil, int cout, int lddy, int splits, int prec,
                      void* stream);
+
+/* ---- layout / plumbing (csrc/elementwise.cu) -------------------------------------------------------------------- */
+int cavp_zero(void* ptr, long long bytes, void* stream);
+/* dst[r][0..c) = value for a [rows][ld] window (zeroing channel slices / gradient pads) */
+int cavp_fill_strided(float* dst, int ld, long long rows, int c, float value, void* stream);
+/* NCHW [n][c][hw] -> NHWC [n][hw][cpad] (channels >= c zero-filled); the model boundary (image, log-mel, OIHW stem
+ * weights).  cavp_nhwc_to_nchw is the inverse for the first c channels. */
+int cavp_nchw_to_nhwc(const float* src, float* dst, int n, int c, int hw, int cpad, void* stream);
+int cavp_nhwc_to_nchw(const float* src, float* dst, int n, int c, int hw, int ld, void* stream);
+/* dst[b][j][i] = src[b][i][j] (weight transposes for dgrad / the InfoNCE gradient GEMM) */
+int cavp_transpose(const float* src, float* dst, int rows, int cols, long long src_ld, long long dst_ld, int batch,
+                   long long src_bs, long long dst_bs, void* stream);
+int cavp_add_inplace(float* dst, const float* src, long long n, float alpha, void* stream);
+/* dst[i] = src[idx[i]] (fea_a[shuffle_idx], models/cavp_model.py:171) or, accumulate_scatter=1, dst[idx[i]] += src[i] */
+int cavp_gather_rows(const float* src, const long long* idx, float* dst, int nrows, int c, int accumulate_scatter,
+                     void* stream);
+
+/* ---- BatchNorm (nn.BatchNorm2d, eps 1e-5, momentum 0.1: encoder_decoder.py:10-11, resnet.py:64-72) --------------
+ * finalize: reduce the igemm `stats` partials -> mean, invstd, scale = gamma*invstd, shift = beta - mean*scale, and the
+ * running-stat update (unbiased variance).  sums_mode: 0 = local statistics; 1 = only export fp64 [2][C] sums to
+ * sums_io (SyncBatchNorm: the host all-reduces them, main_vpo_mono.py:130); 2 = take sums from sums_io. */
+int cavp_bn_finalize(const float* partials, int nparts, int ldstat, int C, double count, const float* gamma,
+                     const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                     float* mean_out, float* invstd_out, float* scale_out, float* shift_out, double* sums_io,
+                     int sums_mode, void* stream);
+int cavp_bn_eval_coeffs(const float* gamma, const float* beta, const float* rm, const float* rv, float eps, int C,
+                        float* scale, float* shift, void* stream);
+/* out = act(y*scale + shift (+ res))   (BN apply + ReLU / LeakyReLU(0.01) + Bottleneck residual, resnet.py:86-96) */
+int cavp_bn_apply(const float* y, int ldy, const float* scale, const float* shift, const float* res, int ldr, float* out,
+                  int ldo, long long rows, int C, int act, float slope, void* stream);
+/* column partial sums of g = dz*act'(z) and g*xhat (xhat from y, mean, invstd; y may be NULL -> plain column sums =
+ * bias gradient); optionally writes g.  partials: [nblk][2][ldp]. */
+int cavp_colreduce(const float* dz, int lddz, const float* z, int ldz, const float* y, int ldy, const float* mean,
+                   const float* invstd, long long rows, int C, int act, float slope, float* gout, int ldg,
+                   float* partials, int ldp, int nblk, void* stream);
+int cavp_partials_sum(const float* partials, int nparts, int ldp, int C, int nk, float* out, void* stream);
+/* dy = gamma*invstd*(g - sum_g/count - xhat*sum_gxhat/count); dres = g (gradient of the residual input) */
+int cavp_bn_bwd_apply(const float* dz, int lddz, const float* z, int ldz, const float* y, int ldy, const float* mean,
+                      const float* invstd, const float* gamma, const float* sums, float inv_count, long long rows, int C,
+                      int act, float slope, float* dy, int lddy, float* dres, int lddres, void* stream);
+
+/* ---- pooling (F.max_pool2d resnet.py:189 / vgg.py:30; ASPP global pooling encoder_decoder.py:158-164;
+ *      AdaptiveMaxPool2d audio_network.py:24) ------------------------------------------------------------------- */
+int cavp_maxpool_fwd(const float* x, int ldx, float* y, int ldy, int* idx, int n, int h, int w, int c, int k,
+                     int stride, int pad, int ho, int wo, void* stream);
+int cavp_maxpool_bwd(const float* dy, int lddy, const int* idx, float* dx, int lddx, long long opix, int c,
+                     void* stream);
+int cavp_pixel_sum(const float* x, int ldx, float* out, int n, int hw, int c, float scale, void* stream);
+int cavp_pixel_bcast(const float* dout, float* dx, int lddx, int n, int hw, int c, float scale, int accumulate,
+                     void* stream);
+int cavp_pixel_max(const float* x, int ldx, float* out, int* arg, int n, int hw, int c, void* stream);
+int cavp_pixel_max_bwd(const float* dout, const int* arg, float* dx, int lddx, int n, int hw, int c, void* stream);
+
+/* ---- bilinear resampling (F.interpolate mode="bilinear": encoder_decoder.py:101 align_corners=True,
+ *      cavp_model.py:140 align_corners=False).  nchw_out=1 writes the full-resolution prediction [n][c][hout][wout].
+ *      The backward is a gather (deterministic); images >= n_valid are known to have zero gradient. */
+int cavp_bilinear_fwd(const float* x, int ldx, int hin, int win, float* y, int ldy, int hout, int wout, int n, int c,
+                      int align_corners, int nchw_out, void* stream);
+int cavp_bilinear_bwd(const float* dy, int lddy, int hout, int wout, float* dx, int lddx, int hin, int win, int n,
+                      int c, int align_corners, int nchw_in, int n_valid, void* stream);
+
+/* ---- fusion (csrc/fusion.cu): nn.LayerNorm (attn.py:133,137,229), the cross-attention core (attn.py:73-106 with a
+ *      single audio key token: sigmoid gate), GELU' (timm Mlp) ------------------------------------------------------ */
+int cavp_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd,
+                       long long T, int C, float eps, void* stream);
+int cavp_layernorm_bwd_nparts(long long T);
+int cavp_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
+                       const float* add, float* dx, float* partials, long long T, int C, void* stream);
+/* q [Bq][N][C]; k, v [Bq*rep][C]; x [Bq*rep][N][C]; attn [Bq*rep][heads][N].  Row r uses q row r % Bq. */
+int cavp_gate_fwd(const float* q, const float* k, const float* v, float* x, float* attn, int Bq, int rep, int N, int C,
+                  int heads, void* stream);
+/* dk, dv must be pre-zeroed [Bq*rep][C] */
+int cavp_gate_bwd(const float* dx, const float* q, const float* k, const float* v, const float* attn, float* dq,
+                  float* dk, float* dv, int Bq, int rep, int N, int C, int heads, void* stream);
+int cavp_gelu_bwd(const float* dy, const float* pre, float* dx, long long n, void* stream);
+
+/* ---- losses (csrc/loss.cu): CrossEntropyLoss(ignore_index) loss/losser.py:60-62; ContrastLoss
+ *      loss/contrastive_aud.py:17-74 -------------------------------------------------------------------------------- */
+int cavp_ce_nblocks(int B, long long HW);
+/* logits NCHW [>=B][C][HW]; labels int64 [B][HW]; loss_and_count = {mean loss, #valid pixels} */
+int cavp_ce_fwd(const float* logits, const long long* labels, int B, int C, long long HW, int ignore_index,
+                float* partials, float* loss_and_count, void* stream);
+int cavp_ce_bwd(const float* logits, const long long* labels, int B, int C, long long HW, int ignore_index,
+                const float* loss_and_count, const float* gscale, float* dlogits, void* stream);
+int cavp_l2norm_gather(const float* f, int ld, const long long* pix, int A, int C, float* anchors, int lda,
+                       float* inv_norm, void* stream);
+int cavp_l2norm_scatter_bwd(const float* danchors, const float* anchors, int lda, const float* inv_norm,
+                            const long long* pix, int A, int C, float* df, int ld, void* stream);
+int cavp_infonce_fwd(const float* S, int lds, const long long* labels, int A, float temperature, float* rowmax,
+                     float* rowneg, float* rowmean, float* loss, void* stream);
+int cavp_infonce_bwd(const float* S, int lds, const long long* labels, int A, float temperature, const float* rowmax,
+                     const float* rowneg, const float* gscale, float* G, int ldg, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,144 @@
+"""Parity of the CUDA product (C-ABI kernels behind cavp_b200.models.CAVP / cavp_b200.trainer.train_step) against
+the golden fixtures produced by the UNMODIFIED reference (tests/golden/*.pt, oracle/make_golden.py) and against the
+oracle on the same seeded inputs.  Bar (BASELINE.json north_star): 1e-3 relative fp32 on logits; bit-exact argmax
+wherever the top-2 margin exceeds the numerical noise."""
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+from conftest import load_golden, rel_err
+from oracle import schema, seeded
+from oracle.make_golden import sample_idx
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3  # north_star tolerance
+# End-to-end gradients of this random-weight, batch-stat-BN network are ill-conditioned in fp32: the reference
+# arithmetic itself (oracle in fp32 vs the same oracle in fp64, tools/grad_sensitivity.py) differs by up to 3.7e-2
+# relative L2 per tensor (median 2.2e-2) because tiny forward perturbations flip ReLU / max-pool decisions, while the
+# gradient norms differ by up to 9e-3.  So end-to-end we assert norms and sampled values within 2x that
+# self-discrepancy; elementwise gradient parity is asserted per op (2e-5) in tests/test_ops_gpu.py.
+GRAD_NORM_TOL = 2e-2  # fp32-vs-fp64 self-discrepancy of the reference arithmetic: up to 9.3e-3
+GRAD_SAMPLE_L2_TOL = 8e-2
+
+
+def build_model(cfg, prec=2):
+    from cavp_b200.models.cavp_model import CAVP
+    args = SimpleNamespace(seg_model="DeepLabV3Plus", last_three_dilation_stride=list(cfg["dilation"]),
+                           audio_backbone=cfg["audio"], num_classes=cfg["nc"], batch_size=cfg["B"], local_rank=0,
+                           cavp_prec=prec)
+    model = CAVP(50, None, num_classes=cfg["nc"], ignore_index=255, audio_backbone_pretrain_path=None,
+                 visual_backbone=50, args=args, in_plane=cfg["in_plane"])
+    sd = schema.seeded_state(cfg["nc"], cfg["audio"], cfg["in_plane"], seed=0)
+    missing, unexpected = model.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+    return model.cuda()
+
+
+def batch_for(cfg):
+    return seeded.synthetic_batch(cfg["B"], cfg["H"], cfg["W"], cfg["nc"], seed=666, audio_frames=cfg["frames"],
+                                  in_plane=cfg["in_plane"])
+
+
+def test_state_dict_keys_match_reference_schema():
+    cfg = load_golden("tiny_train")["config"]
+    model = build_model(cfg)
+    ref_keys = list(schema.cavp_schema(cfg["nc"], cfg["audio"], cfg["in_plane"]).shapes.keys())
+    assert sorted(model.state_dict().keys()) == sorted(ref_keys)
+
+
+def test_eval_cfgA_matches_reference_golden():
+    g = load_golden("cfgA_eval_224")
+    cfg = g["config"]
+    model = build_model(cfg).eval()
+    batch = batch_for(cfg)
+    pred, fusion, pack = model(batch["image"].cuda(), batch["audio"][:cfg["B"]].cuda(), eval_mode=True)
+    assert pred.shape == (1, 71, 224, 224) and fusion.shape == (1, 304, 56, 56)
+    assert pack["attn_v"].shape == (1, 4, 3136, 1) and pack["audio"].shape == (1, 304, 1, 1)
+    e_pred = rel_err(pred[:, :, ::4, ::4], g["pred_stride4"])
+    e_fus = rel_err(fusion[:, :, ::2, ::2], g["fusion_stride2"])
+    e_att = rel_err(pack["attn_v"], g["attn_v"])
+    print("eval cfgA rel err: pred %.2e fusion %.2e attn %.2e" % (e_pred, e_fus, e_att))
+    assert e_pred < TOL and e_fus < TOL and e_att < TOL
+    am = pred.argmax(1).to(torch.uint8).cpu()
+    safe = g["margin"].float() > 2e-3 * g["pred_summary"]["absmax"]
+    assert torch.equal(am[safe], g["argmax"][safe])  # bit-exact argmax outside the noise margin
+    mismatch = float((am != g["argmax"]).float().mean())
+    print("argmax mismatch rate %.2e" % mismatch)
+    assert mismatch < 1e-3
+
+
+@pytest.mark.parametrize("name", ["tiny_train", "tiny_train_fff71", "tiny_train_r18_stereo", "cfgB_train_224"])
+def test_train_step_matches_reference_golden(name):
+    from cavp_b200.trainer import shuffled_labels, train_step
+    g = load_golden(name)
+    cfg = g["config"]
+    model = build_model(cfg).train()
+    batch = batch_for(cfg)
+    B = cfg["B"]
+    spl = shuffled_labels(batch["pix_label"], batch["img_label"], batch["shuffle_idx"])
+    assert torch.equal(spl, seeded.shuffled_labels(batch["pix_label"], batch["img_label"], batch["shuffle_idx"]))
+    audio = batch["audio"][:B] if cfg["audio_func"] else batch["audio"]
+    torch.manual_seed(1234)  # make_golden seeds the CPU generator right before ContrastLoss
+    res = train_step(model, batch["image"].cuda(), audio.cuda(), batch["pix_label"], spl, max_views=cfg["max_views"],
+                     shuffle_idx=batch["shuffle_idx"].cuda() if cfg["audio_func"] else None,
+                     audio_func=cfg["audio_func"], keep_outputs=True)
+    ps, fs, at = g["pred_stride"], g["fusion_stride"], g["attn_stride"]
+    errs = dict(pred=rel_err(res.out_pred[:, :, ::ps, ::ps], g["pred"]),
+                fusion=rel_err(res.out_fusion[:, :, ::fs, ::fs], g["fusion"]),
+                attn=rel_err(res.attn_v[:, :, ::at], g["attn_v"]), audio=rel_err(res.audio, g["audio"]),
+                l_ce=abs(float(res.l_ce) - g["l_ce"]) / abs(g["l_ce"]),
+                l_ctr=abs(float(res.l_ctr) - g["l_ctr"]) / abs(g["l_ctr"]))
+    print(name, {k: "%.2e" % v for k, v in errs.items()})
+    for k, v in errs.items():
+        assert v < TOL, (k, v)
+    sd = model.state_dict()
+    for k, v in g["buffers"].items():
+        assert rel_err(sd[k].float(), v.float()) < TOL, k
+    worst, worst_n = (0.0, ""), (0.0, "")
+    params = dict(model.named_parameters())
+    for k, gs in g["grads"].items():
+        p = params[k]
+        if gs is None:
+            assert p.grad is None, k
+            continue
+        assert p.grad is not None, k
+        gr = p.grad.detach().cpu().contiguous()
+        got = gr.flatten()[sample_idx(gr.numel())].double()
+        ref = gs["samples"].double()
+        e = float((got - ref).norm()) / max(float(ref.norm()), 1e-3 * gs["absmax"] * ref.numel() ** 0.5, 1e-30)
+        ne = abs(float(gr.double().norm()) - gs["norm"]) / (gs["norm"] + 1e-30)
+        worst = max(worst, (e, k))
+        worst_n = max(worst_n, (ne, k))
+        assert e < GRAD_SAMPLE_L2_TOL and ne < GRAD_NORM_TOL, (k, e, ne)
+    print(name, "worst grad sample-L2 %.2e (%s); worst norm err %.2e (%s)" % (worst + worst_n))
+
+
+def test_module_autograd_path_equals_train_step():
+    """nn.Module forward + torch-side slicing + cavp_b200 losses (the drop-in usage) == fused train_step."""
+    from cavp_b200.loss import ContrastLoss, CrossEntropyLoss
+    from cavp_b200.trainer import shuffled_labels, train_step
+    cfg = load_golden("tiny_train")["config"]
+    batch = batch_for(cfg)
+    B = cfg["B"]
+    spl = shuffled_labels(batch["pix_label"], batch["img_label"], batch["shuffle_idx"])
+    m1 = build_model(cfg).train()
+    torch.manual_seed(1234)
+    r = train_step(m1, batch["image"].cuda(), batch["audio"].cuda(), batch["pix_label"], spl, max_views=cfg["max_views"])
+    m2 = build_model(cfg).train()
+    out_cat, ctr_cat, pack = m2(batch["image"].cuda(), batch["audio"].cuda(), None, False)
+    assert out_cat.shape == (2 * B, cfg["nc"], cfg["H"], cfg["W"]) and pack["visual"].shape == ctr_cat.shape
+    output = out_cat[:B] + out_cat[B:] * 0.0  # trainer_cavp_vpo_mono.py:171
+    torch.manual_seed(1234)
+    l_ctr = ContrastLoss(0.1, 255, cfg["max_views"])(ctr_cat[:B], batch["pix_label"].cuda(), ctr_cat[B:], spl.cuda())
+    l_ce = CrossEntropyLoss(255)(output, batch["pix_label"].cuda())
+    (l_ce + l_ctr).backward()
+    assert abs(float(l_ce) - float(r.l_ce)) < 1e-5 * abs(float(r.l_ce))
+    assert abs(float(l_ctr) - float(r.l_ctr)) < 1e-5 * abs(float(r.l_ctr))
+    for (k, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert (p1.grad is None) == (p2.grad is None), k
+        if p1.grad is not None:
+            # same kernels; split-K / pooling atomics reorder fp32 sums run to run and the network amplifies that
+            a, b = p2.grad.double().flatten(), p1.grad.double().flatten()
+            assert float((a - b).norm() / b.norm().clamp_min(1e-30)) < GRAD_SAMPLE_L2_TOL, k
+            assert abs(float(a.norm() - b.norm())) / float(b.norm().clamp_min(1e-30)) < GRAD_NORM_TOL, k

@@ -21,7 +21,7 @@ def igemm(x, w, nimg, hs, ws, c, ho, wo, r, s, stride, pad, dil, dgrad, ncols, p
     st = torch.zeros(((M + 127) // 128) * 4, 2, ncols, device=dev) if stats else None
     _C.call("cavp_igemm", _C.ptr(x), _C.ptr(w), _C.ptr(y), _C.ptr(yp), _C.ptr(scale), _C.ptr(shift), _C.ptr(res),
             _C.ptr(st), nimg, hs, ws, c, x.shape[-1], ho, wo, r, s, stride, pad, dil, dgrad, ncols, w.shape[-1] if w.dim() == 2 else r * s * c,
-            ldy, res.shape[-1] if res is not None else 0, 0, ncols, act, 0.01, splits, prec, _C.stream())
+            ldy, res.shape[-1] if res is not None else 0, 0, 0, ncols, act, 0.01, splits, prec, _C.stream())
     torch.cuda.synchronize()
     return y, yp, st
 
@@ -133,7 +133,7 @@ for (nimg, h, c, cout, r, pad) in [(64, 56, 256, 256, 3, 1), (64, 56, 304, 256, 
     for prec in (1, 2):
         def run():
             _C.call("cavp_igemm", _C.ptr(xh), _C.ptr(wh), _C.ptr(y), 0, 0, 0, 0, 0, nimg, h, h, c, c, h, h, r, r, 1, pad, pad if r == 3 else 1, 0,
-                    cout, r * r * c, cout, 0, 0, cout, 0, 0.0, 1, prec, _C.stream())
+                    cout, r * r * c, cout, 0, 0, 0, cout, 0, 0.0, 1, prec, _C.stream())
         ms = bench(run)
         fl = 2.0 * M * cout * r * r * c
         speeds[f"fwd n{nimg} {h}^2 c{c}->{cout} k{r} prec{prec}"] = dict(ms=ms, tflops=fl / ms / 1e9)
