@@ -1,13 +1,43 @@
 // C-ABI launchers for the tcgen05 implicit-GEMM kernels (igemm.cuh).  See include/cavp_b200.h for the contract.
+#include <cstring>
 #include "igemm.cuh"
 #include "../../include/cavp_b200.h"
 
 namespace cavp {
 
-template <int BN, int PREC, int MODE>
-static int launch_igemm(const IgemmParams& p, cudaStream_t st) {
+// ---- TMA descriptors for the weight operand (driver entry point resolved through the runtime; no -lcuda needed)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  }
+  return fn;
+}
+// [rows][ld] fp32 matrix, box = 32 (K) x bn rows, 128-byte swizzle, out-of-bounds elements read as zero
+static int make_weight_tmap(CUtensorMap* tm, const float* w, int rows, int K, int ld, int bn) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return CAVP_ERR_ARG;
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * 4};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(bn)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(w), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 1000 + static_cast<int>(r);
+}
+
+template <int BN, int PREC, int MODE, bool BTMA>
+static int launch_igemm(const IgemmParams& p, const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, cudaStream_t st) {
   using Cfg = TileCfg<BN, PREC>;
-  auto kern = igemm_kernel<BN, PREC, MODE>;
+  auto kern = igemm_kernel<BN, PREC, MODE, BTMA>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -16,16 +46,49 @@ static int launch_igemm(const IgemmParams& p, cudaStream_t st) {
   }
   const int m_tiles = (p.M + BM - 1) / BM;
   dim3 grid(static_cast<unsigned>(m_tiles * p.n_tiles), static_cast<unsigned>(p.splits), 1);
-  kern<<<grid, CTA_THREADS, Cfg::SMEM_BYTES, st>>>(p);
+  kern<<<grid, CTA_THREADS, Cfg::SMEM_BYTES, st>>>(p, tm_hi, tm_lo);
   return static_cast<int>(cudaGetLastError());
 }
 
+// b_lo_off > 0: the B operand is pre-split ([hi | lo], lo at w + b_lo_off) and is fetched by TMA
 template <int MODE>
-static int dispatch(IgemmParams& p, int prec, cudaStream_t st) {
+static int dispatch(IgemmParams& p, int prec, long long b_lo_off, cudaStream_t st) {
   const int bn = p.Ncols > 64 ? 128 : 64;
   p.n_tiles = (p.Ncols + bn - 1) / bn;
-  if (prec == 2) return bn == 128 ? launch_igemm<128, 2, MODE>(p, st) : launch_igemm<64, 2, MODE>(p, st);
-  return bn == 128 ? launch_igemm<128, 1, MODE>(p, st) : launch_igemm<64, 1, MODE>(p, st);
+  CUtensorMap tm_hi, tm_lo;
+  memset(&tm_hi, 0, sizeof(tm_hi));
+  memset(&tm_lo, 0, sizeof(tm_lo));
+  if constexpr (MODE == MODE_ROW) {
+    if (b_lo_off > 0) {
+      int rc = make_weight_tmap(&tm_hi, p.w, p.Ncols, p.K, p.ldw, bn);
+      if (rc) return rc;
+      rc = make_weight_tmap(&tm_lo, p.w + b_lo_off, p.Ncols, p.K, p.ldw, bn);
+      if (rc) return rc;
+      if (prec == 2)
+        return bn == 128 ? launch_igemm<128, 2, MODE, true>(p, tm_hi, tm_lo, st)
+                         : launch_igemm<64, 2, MODE, true>(p, tm_hi, tm_lo, st);
+      return bn == 128 ? launch_igemm<128, 1, MODE, true>(p, tm_hi, tm_lo, st)
+                       : launch_igemm<64, 1, MODE, true>(p, tm_hi, tm_lo, st);
+    }
+  }
+  if (prec == 2)
+    return bn == 128 ? launch_igemm<128, 2, MODE, false>(p, tm_hi, tm_lo, st)
+                     : launch_igemm<64, 2, MODE, false>(p, tm_hi, tm_lo, st);
+  return bn == 128 ? launch_igemm<128, 1, MODE, false>(p, tm_hi, tm_lo, st)
+                   : launch_igemm<64, 1, MODE, false>(p, tm_hi, tm_lo, st);
+}
+
+// hi = rn_tf32(w), lo = rn_tf32(w - hi): done once per step per weight instead of once per CTA per k-block
+__global__ void split_tf32_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo,
+                                  long long n4) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(w)[i];
+    const float h0 = tf32_rn(v.x), h1 = tf32_rn(v.y), h2 = tf32_rn(v.z), h3 = tf32_rn(v.w);
+    reinterpret_cast<float4*>(hi)[i] = make_float4(h0, h1, h2, h3);
+    reinterpret_cast<float4*>(lo)[i] =
+        make_float4(tf32_rn(v.x - h0), tf32_rn(v.y - h1), tf32_rn(v.z - h2), tf32_rn(v.w - h3));
+  }
 }
 
 static void fill_divs(IgemmParams& p) {
@@ -43,8 +106,7 @@ extern "C" int cavp_igemm(const float* x, const float* w, float* y, float* y_pre
                           const float* shift, const float* res, float* stats, int nimg, int hs, int ws, int c, int ldx,
                           int ho, int wo, int r, int s, int stride, int pad, int dil, int dgrad, int ncols, int ldw,
                           int ldy, int ldr, int res_mod, int res_div, int ldstat, int act, float slope, int splits,
-                          int prec,
-                          void* stream) {
+                          int prec, long long b_lo_off, void* stream) {
   if (!x || !w || !y) return CAVP_ERR_NULL;
   if ((c & 3) || (ldx & 3) || (ldw & 3) || c <= 0 || ncols <= 0) return CAVP_ERR_ALIGN;
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 15)) return CAVP_ERR_ALIGN;
@@ -63,7 +125,8 @@ extern "C" int cavp_igemm(const float* x, const float* w, float* y, float* y_pre
   p.splits = splits < 1 ? 1 : (splits > p.num_kb ? p.num_kb : splits);
   if (p.splits > 1 && (y_pre || scale || shift || res || stats || act != ACT_NONE)) return CAVP_ERR_ARG;
   fill_divs(p);
-  return dispatch<MODE_ROW>(p, prec, static_cast<cudaStream_t>(stream));
+  if (b_lo_off > 0 && ((b_lo_off & 3) || (reinterpret_cast<uintptr_t>(w) & 15))) return CAVP_ERR_ALIGN;
+  return dispatch<MODE_ROW>(p, prec, b_lo_off, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int cavp_igemm_wgrad(const float* dy, const float* x, float* dw, int nimg, int hs, int ws, int c, int ldx,
@@ -84,5 +147,16 @@ extern "C" int cavp_igemm_wgrad(const float* dy, const float* x, float* dw, int 
   p.num_kb = (p.red_len + BK - 1) / BK;
   p.splits = splits < 1 ? 1 : (splits > p.num_kb ? p.num_kb : splits);
   fill_divs(p);
-  return dispatch<MODE_WGRAD>(p, prec, static_cast<cudaStream_t>(stream));
+  return dispatch<MODE_WGRAD>(p, prec, 0, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int cavp_split_tf32(const float* w, float* hi, float* lo, long long n, void* stream) {
+  if ((n & 3) || (reinterpret_cast<uintptr_t>(w) & 15) || (reinterpret_cast<uintptr_t>(hi) & 15) ||
+      (reinterpret_cast<uintptr_t>(lo) & 15))
+    return CAVP_ERR_ALIGN;
+  long long blocks = (n / 4 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  split_tf32_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(w, hi, lo, n / 4);
+  return static_cast<int>(cudaGetLastError());
 }

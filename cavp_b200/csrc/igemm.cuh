@@ -19,6 +19,7 @@
 // pulled out of a 4-deep TMEM ring with tcgen05.ld and added, round-to-nearest, into fp32 registers by the
 // producer warps while their next global loads are in flight.
 #pragma once
+#include <cuda.h>
 #include "ptx.cuh"
 
 namespace cavp {
@@ -65,7 +66,7 @@ struct TileCfg {
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * PREC;
   static constexpr int STAGES = (PREC == 2) ? (BN >= 128 ? 3 : 4) : 4;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*row table*/;
   static constexpr int TMEM_COLS = NBUF * BN < 32 ? 32 : NBUF * BN;
   static constexpr int HALF = BN / 2;  // accumulator columns owned by one epilogue thread
 };
@@ -103,8 +104,10 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-template <int BN, int PREC, int MODE>
-__global__ void __maxnreg__(224) igemm_kernel(const IgemmParams p) {
+template <int BN, int PREC, int MODE, bool BTMA>
+__global__ void __launch_bounds__(CTA_THREADS, 1)
+igemm_kernel(const IgemmParams p, const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo) {
+  static_assert(!BTMA || MODE == MODE_ROW, "TMA B operand only for the row-major (weights) mode");
   using Cfg = TileCfg<BN, PREC>;
   constexpr bool PROMOTE = Cfg::PROMOTE;
   constexpr int NBUF = Cfg::NBUF;
@@ -120,6 +123,7 @@ __global__ void __maxnreg__(224) igemm_kernel(const IgemmParams p) {
   uint64_t* accf_bar = bars + 2 * Cfg::STAGES;           // [NBUF]    MMA -> promotion
   uint64_t* acce_bar = bars + 2 * Cfg::STAGES + NBUF;    // [NBUF]    promotion -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 2 * NBUF);
+  int2* rowtab = reinterpret_cast<int2*>(smem_aligned + Cfg::STAGES * Cfg::STAGE_BYTES + 256);  // [BM] (pixel base, packed y/x)
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -138,7 +142,7 @@ __global__ void __maxnreg__(224) igemm_kernel(const IgemmParams p) {
 
   if (tid == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
-      mbar_init(&full_bar[s], GROUP_THREADS);
+      mbar_init(&full_bar[s], GROUP_THREADS + (BTMA ? 1 : 0));
       mbar_init(&empty_bar[s], 1);
     }
     for (int b = 0; b < NBUF; ++b) {
@@ -146,6 +150,29 @@ __global__ void __maxnreg__(224) igemm_kernel(const IgemmParams p) {
       mbar_init(&acce_bar[b], PRODUCER_THREADS);
     }
     fence_mbar_init();
+  }
+  if (MODE == MODE_ROW && tid < BM) {
+    const int m = m0 + tid;
+    int2 e = make_int2(-1, 0);
+    if (m < p.M) {
+      uint32_t n, rem, oy, ox;
+      p.div_howo.divmod(static_cast<uint32_t>(m), n, rem);
+      p.div_wo.divmod(rem, oy, ox);
+      int ybase, xbase;
+      if (p.dgrad) {
+        ybase = static_cast<int>(oy) + p.pad;
+        xbase = static_cast<int>(ox) + p.pad;
+      } else {
+        ybase = static_cast<int>(oy) * p.stride - p.pad;
+        xbase = static_cast<int>(ox) * p.stride - p.pad;
+      }
+      e = make_int2(static_cast<int>(n) * p.Hs * p.Ws, ((ybase + 0x4000) << 16) | (xbase + 0x4000));
+    }
+    rowtab[tid] = e;
+  }
+  if (BTMA && tid == 32) {
+    tma_prefetch_desc(&tm_b_hi);
+    if (PREC == 2) tma_prefetch_desc(&tm_b_lo);
   }
   if (warp == 8) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   tc_fence_before();
@@ -167,13 +194,13 @@ __global__ void __maxnreg__(224) igemm_kernel(const IgemmParams p) {
       mbar_wait(&accf_bar[b], PROMOTE ? ((u / NBUF) & 1) : 0);
       tc_fence_after();
 #pragma unroll
-      for (int cgrp = 0; cgrp < HALF / 32; ++cgrp) {
-        float v[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                      static_cast<uint32_t>(b * BN + group * HALF + cgrp * 32),
+      for (int cgrp = 0; cgrp < HALF / 16; ++cgrp) {
+        float v[16];
+        tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                      static_cast<uint32_t>(b * BN + group * HALF + cgrp * 16),
                   v);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[cgrp * 32 + j] += v[j];
+        for (int j = 0; j < 16; ++j) acc[cgrp * 16 + j] += v[j];
       }
       if (PROMOTE) {
         tc_fence_before();
@@ -189,35 +216,11 @@ __global__ void __maxnreg__(224) igemm_kernel(const IgemmParams p) {
     const uint32_t swz = static_cast<uint32_t>((c ^ (r0 & 7)) << 4);
     const int cc = gtid & 31;
     const int rr = gtid >> 5;
-    int nb[8], yx[8];  // yx packs (ybase + 0x4000) << 16 | (xbase + 0x4000)
     // wgrad per-thread constants
     int wg_co = 0, wg_dy = 0, wg_dx = 0;
     uint32_t wg_ci = 0;
     bool wg_co_ok = false, wg_j_ok = false;
-    if (MODE == MODE_ROW) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int m = m0 + r0 + 16 * i;
-        if (m < p.M) {
-          uint32_t n, rem, oy, ox;
-          p.div_howo.divmod(static_cast<uint32_t>(m), n, rem);
-          p.div_wo.divmod(rem, oy, ox);
-          nb[i] = static_cast<int>(n) * p.Hs * p.Ws;
-          int ybase, xbase;
-          if (p.dgrad) {
-            ybase = static_cast<int>(oy) + p.pad;
-            xbase = static_cast<int>(ox) + p.pad;
-          } else {
-            ybase = static_cast<int>(oy) * p.stride - p.pad;
-            xbase = static_cast<int>(ox) * p.stride - p.pad;
-          }
-          yx[i] = ((ybase + 0x4000) << 16) | (xbase + 0x4000);
-        } else {
-          nb[i] = -1;
-          yx[i] = 0;
-        }
-      }
-    } else {
+    if (MODE == MODE_WGRAD) {
       wg_co = m0 + cc * 4;
       wg_co_ok = wg_co < p.M;
       const int j = n0 + cc * 4;
@@ -229,109 +232,161 @@ __global__ void __maxnreg__(224) igemm_kernel(const IgemmParams p) {
       wg_dx = static_cast<int>(kx) * p.dil - p.pad;
     }
 
-    const int npairs = (nkb + 1) >> 1;
-    for (int u = 0; u < npairs; ++u) {
-      const int it = 2 * u + group;
-      const bool active = it < nkb;
-      const int s = it % Cfg::STAGES;
-      float4 va[8];
-      float4 vb[8];
-      if (active) {
-        mbar_wait(&empty_bar[s], (((it / Cfg::STAGES) & 1) ^ 1));
-        if (MODE == MODE_ROW) {
-          const int k = (kb_begin + it) * BK + c * 4;
-          const bool kvalid = k < p.K;
-          uint32_t tap, ci, ky, kx;
-          p.div_c.divmod(static_cast<uint32_t>(kvalid ? k : 0), tap, ci);
-          p.div_s.divmod(tap, ky, kx);
-          const int dy = static_cast<int>(ky) * p.dil;
-          const int dx = static_cast<int>(kx) * p.dil;
+    // ---- operand movers
+    auto load_row_a = [&](int it, float4 (&va)[8]) {
+      const int k = (kb_begin + it) * BK + c * 4;
+      const bool kvalid = k < p.K;
+      uint32_t tap, ci, ky, kx;
+      p.div_c.divmod(static_cast<uint32_t>(kvalid ? k : 0), tap, ci);
+      p.div_s.divmod(tap, ky, kx);
+      const int dy = static_cast<int>(ky) * p.dil;
+      const int dx = static_cast<int>(kx) * p.dil;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            int iy, ix;
-            bool ok = kvalid && nb[i] >= 0;
-            const int ybase = (yx[i] >> 16) - 0x4000, xbase = (yx[i] & 0xFFFF) - 0x4000;
-            if (p.dgrad) {
-              iy = ybase - dy;
-              ix = xbase - dx;
-              if (p.stride > 1) {
-                ok = ok && iy >= 0 && ix >= 0 && (iy % p.stride) == 0 && (ix % p.stride) == 0;
-                iy /= p.stride;
-                ix /= p.stride;
-              }
-            } else {
-              iy = ybase + dy;
-              ix = xbase + dx;
-            }
-            ok = ok && static_cast<unsigned>(iy) < static_cast<unsigned>(p.Hs) &&
-                 static_cast<unsigned>(ix) < static_cast<unsigned>(p.Ws);
-            va[i] = ok ? ldg_nc_v4(p.x + static_cast<size_t>(nb[i] + iy * p.Ws + ix) * p.ldx + ci)
-                       : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-#pragma unroll
-          for (int j = 0; j < BN / 16; ++j) {
-            const int n = n0 + r0 + 16 * j;
-            vb[j] = (kvalid && n < p.Ncols) ? ldg_nc_v4(p.w + static_cast<size_t>(n) * p.ldw + k)
-                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < 8; ++i) {
+        int iy, ix;
+        const int2 ri = rowtab[r0 + 16 * i];
+        bool ok = kvalid && ri.x >= 0;
+        const int ybase = (ri.y >> 16) - 0x4000, xbase = (ri.y & 0xFFFF) - 0x4000;
+        if (p.dgrad) {
+          iy = ybase - dy;
+          ix = xbase - dx;
+          if (p.stride > 1) {
+            ok = ok && iy >= 0 && ix >= 0 && (iy % p.stride) == 0 && (ix % p.stride) == 0;
+            iy /= p.stride;
+            ix /= p.stride;
           }
         } else {
-          const int pix0 = (kb_begin + it) * BK;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int pix = pix0 + rr + 4 * i;
-            const bool pok = pix < p.red_len;
-            va[i] = (pok && wg_co_ok) ? ldg_nc_v4(p.w + static_cast<size_t>(pix) * p.ldw + wg_co)
-                                      : make_float4(0.f, 0.f, 0.f, 0.f);
-            bool ok = pok && wg_j_ok;
-            uint32_t n = 0, rem, oy = 0, ox = 0;
-            if (ok) {
-              p.div_howo.divmod(static_cast<uint32_t>(pix), n, rem);
-              p.div_wo.divmod(rem, oy, ox);
-            }
-            const int iy = static_cast<int>(oy) * p.stride + wg_dy;
-            const int ix = static_cast<int>(ox) * p.stride + wg_dx;
-            ok = ok && static_cast<unsigned>(iy) < static_cast<unsigned>(p.Hs) &&
-                 static_cast<unsigned>(ix) < static_cast<unsigned>(p.Ws);
-            vb[i] = ok ? ldg_nc_v4(p.x +
-                                   (static_cast<size_t>(n) * p.Hs * p.Ws + static_cast<size_t>(iy) * p.Ws + ix) *
-                                       p.ldx +
-                                   wg_ci)
-                       : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+          iy = ybase + dy;
+          ix = xbase + dx;
         }
+        ok = ok && static_cast<unsigned>(iy) < static_cast<unsigned>(p.Hs) &&
+             static_cast<unsigned>(ix) < static_cast<unsigned>(p.Ws);
+        va[i] = ok ? ldg_nc_v4(p.x + static_cast<size_t>(ri.x + iy * p.Ws + ix) * p.ldx + ci)
+                   : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      if (PROMOTE && u >= 2) promote(u - 2);  // overlaps with the global loads issued above
-      if (active) {
-        const uint32_t stage = smem_base + s * Cfg::STAGE_BYTES;
-        const uint32_t a_hi = stage, a_lo = stage + Cfg::A_BYTES;
-        const uint32_t b_hi = stage + Cfg::A_BYTES * PREC, b_lo = b_hi + Cfg::B_BYTES;
-        if (MODE == MODE_ROW) {
+    };
+    auto load_row_b = [&](int it, float4 (&vb)[8]) {
+      const int k = (kb_begin + it) * BK + c * 4;
+      const bool kvalid = k < p.K;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const uint32_t off = static_cast<uint32_t>((r0 + 16 * i) * 128) + swz;
-            store_split<PREC>(a_hi + off, a_lo + off, va[i]);
+      for (int j = 0; j < BN / 16; ++j) {
+        const int n = n0 + r0 + 16 * j;
+        vb[j] = (kvalid && n < p.Ncols) ? ldg_nc_v4(p.w + static_cast<size_t>(n) * p.ldw + k)
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    auto load_wgrad = [&](int it, float4 (&va)[8], float4 (&vb)[8]) {
+      const int pix0 = (kb_begin + it) * BK;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int pix = pix0 + rr + 4 * i;
+        const bool pok = pix < p.red_len;
+        va[i] = (pok && wg_co_ok) ? ldg_nc_v4(p.w + static_cast<size_t>(pix) * p.ldw + wg_co)
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+        bool ok = pok && wg_j_ok;
+        uint32_t n = 0, rem, oy = 0, ox = 0;
+        if (ok) {
+          p.div_howo.divmod(static_cast<uint32_t>(pix), n, rem);
+          p.div_wo.divmod(rem, oy, ox);
+        }
+        const int iy = static_cast<int>(oy) * p.stride + wg_dy;
+        const int ix = static_cast<int>(ox) * p.stride + wg_dx;
+        ok = ok && static_cast<unsigned>(iy) < static_cast<unsigned>(p.Hs) &&
+             static_cast<unsigned>(ix) < static_cast<unsigned>(p.Ws);
+        vb[i] = ok ? ldg_nc_v4(p.x +
+                               (static_cast<size_t>(n) * p.Hs * p.Ws + static_cast<size_t>(iy) * p.Ws + ix) * p.ldx +
+                               wg_ci)
+                   : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    auto store_row_a = [&](int s, const float4 (&va)[8]) {
+      const uint32_t a_hi = smem_base + s * Cfg::STAGE_BYTES, a_lo = a_hi + Cfg::A_BYTES;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t off = static_cast<uint32_t>((r0 + 16 * i) * 128) + swz;
+        store_split<PREC>(a_hi + off, a_lo + off, va[i]);
+      }
+    };
+    auto store_row_b = [&](int s, const float4 (&vb)[8]) {
+      const uint32_t b_hi = smem_base + s * Cfg::STAGE_BYTES + Cfg::A_BYTES * PREC, b_lo = b_hi + Cfg::B_BYTES;
+#pragma unroll
+      for (int j = 0; j < BN / 16; ++j) {
+        const uint32_t off = static_cast<uint32_t>((r0 + 16 * j) * 128) + swz;
+        store_split<PREC>(b_hi + off, b_lo + off, vb[j]);
+      }
+    };
+    // MN-major tf32 operands use the 128B swizzle with a 32-byte base: atom = 4 k-rows x 128 B, the 32-byte chunk
+    // index is XORed with (k-row & 3).
+    auto store_wgrad = [&](int s, const float4 (&va)[8], const float4 (&vb)[8]) {
+      const uint32_t a_hi = smem_base + s * Cfg::STAGE_BYTES, a_lo = a_hi + Cfg::A_BYTES;
+      const uint32_t b_hi = a_hi + Cfg::A_BYTES * PREC, b_lo = b_hi + Cfg::B_BYTES;
+      const uint32_t atom_off = static_cast<uint32_t>((cc >> 3) * 4096);
+      const int c16 = cc & 7;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = rr + 4 * i;
+        const uint32_t off = atom_off + static_cast<uint32_t>(r * 128) +
+                             static_cast<uint32_t>((((c16 >> 1) ^ (r & 3)) << 5) | ((c16 & 1) << 4));
+        store_split<PREC>(a_hi + off, a_lo + off, va[i]);
+        if (cc * 4 < BN) store_split<PREC>(b_hi + off, b_lo + off, vb[i]);
+      }
+    };
+
+    const int npairs = (nkb + 1) >> 1;
+    if (BTMA) {
+      // B (pre-split weights) arrives by TMA; A is register double-buffered: the global loads of k-block it+2 are
+      // in flight while k-block it is promoted / split / stored.
+      float4 va0[8], va1[8];
+      auto body = [&](int u, float4 (&cur)[8], float4 (&nxt)[8]) {
+        const int it = 2 * u + group;
+        if (it + 2 < nkb) load_row_a(it + 2, nxt);
+        if (PROMOTE && u >= 2) promote(u - 2);
+        if (it < nkb) {
+          const int s = it % Cfg::STAGES;
+          mbar_wait(&empty_bar[s], (((it / Cfg::STAGES) & 1) ^ 1));
+          if (gtid == 0) {
+            const uint32_t b_hi = smem_base + s * Cfg::STAGE_BYTES + Cfg::A_BYTES * PREC;
+            mbar_arrive_expect_tx(&full_bar[s], Cfg::B_BYTES * PREC);
+            tma_load_2d(b_hi, &tm_b_hi, &full_bar[s], (kb_begin + it) * BK, n0);
+            if (PREC == 2) tma_load_2d(b_hi + Cfg::B_BYTES, &tm_b_lo, &full_bar[s], (kb_begin + it) * BK, n0);
           }
-#pragma unroll
-          for (int j = 0; j < BN / 16; ++j) {
-            const uint32_t off = static_cast<uint32_t>((r0 + 16 * j) * 128) + swz;
-            store_split<PREC>(b_hi + off, b_lo + off, vb[j]);
-          }
-        } else {
-          // MN-major tf32 operands use the 128B swizzle with a 32-byte base: atom = 4 k-rows x 128 B, the 32-byte
-          // chunk index is XORed with (k-row & 3).
-          const uint32_t atom_off = static_cast<uint32_t>((cc >> 3) * 4096);
-          const int c16 = cc & 7;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = rr + 4 * i;
-            const uint32_t off = atom_off + static_cast<uint32_t>(r * 128) +
-                                 static_cast<uint32_t>((((c16 >> 1) ^ (r & 3)) << 5) | ((c16 & 1) << 4));
-            store_split<PREC>(a_hi + off, a_lo + off, va[i]);
-            if (cc * 4 < BN) store_split<PREC>(b_hi + off, b_lo + off, vb[i]);
+          store_row_a(s, cur);
+          fence_proxy_async();
+          mbar_arrive(&full_bar[s]);
+        }
+      };
+      if (group < nkb) load_row_a(group, va0);
+      for (int u = 0; u < npairs; u += 2) {
+        body(u, va0, va1);
+        if (u + 1 < npairs) body(u + 1, va1, va0);
+      }
+    } else {
+      for (int u = 0; u < npairs; ++u) {
+        const int it = 2 * u + group;
+        const bool active = it < nkb;
+        const int s = it % Cfg::STAGES;
+        float4 va[8];
+        float4 vb[8];
+        if (active) {
+          mbar_wait(&empty_bar[s], (((it / Cfg::STAGES) & 1) ^ 1));
+          if (MODE == MODE_ROW) {
+            load_row_a(it, va);
+            load_row_b(it, vb);
+          } else {
+            load_wgrad(it, va, vb);
           }
         }
-        fence_proxy_async();
-        mbar_arrive(&full_bar[s]);
+        if (PROMOTE && u >= 2) promote(u - 2);  // overlaps with the global loads issued above
+        if (active) {
+          if (MODE == MODE_ROW) {
+            store_row_a(s, va);
+            store_row_b(s, vb);
+          } else {
+            store_wgrad(s, va, vb);
+          }
+          fence_proxy_async();
+          mbar_arrive(&full_bar[s]);
+        }
       }
     }
     if (PROMOTE) {

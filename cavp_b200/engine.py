@@ -101,6 +101,25 @@ class WeightRef:
             wk = wp
         self.wk = wk
         self._wt = None
+        self._split = None
+        self._wt_split = None
+
+    def _presplit(self, w):
+        """[hi | lo] TF32 split of a K-major operand, done once per step; the igemm kernel then fetches it by TMA."""
+        sp = self.g.empty(2, w.shape[0], w.shape[1])
+        self.g.call("cavp_split_tf32", w.data_ptr(), sp[0].data_ptr(), sp[1].data_ptr(), w.numel())
+        return sp
+
+    def operand(self):
+        """(tensor, lo offset in elements) for cavp_igemm's B operand."""
+        if self._split is None:
+            self._split = self._presplit(self.wk)
+        return self._split, self.wk.numel()
+
+    def operand_t(self):
+        if self._wt_split is None:
+            self._wt_split = self._presplit(self.transposed())
+        return self._wt_split, self._wt.numel()
 
     def transposed(self):
         """[Cin][taps][Cout_eff] for the data-gradient GEMM."""
@@ -246,11 +265,14 @@ class Graph:
         """geom = (ho, wo, r, s, stride, pad, dil).  x: A-operand source Act; y: output Act (rows = x.n*ho*wo)."""
         ho, wo, r, s, stride, pad, dil = geom
         hs, ws = (x.h, x.w) if src_hw is None else src_hw
+        b_lo_off = 0
+        if isinstance(wk, tuple):  # pre-split weight operand -> TMA path
+            wk, b_lo_off = wk
         self.work(flops=2.0 * x.n * ho * wo * ncols * r * s * x.c)
         self.call("cavp_igemm", x.ptr, wk.data_ptr(), y.ptr, 0 if y_pre is None else y_pre.ptr, _C.ptr(scale),
                   _C.ptr(shift), 0 if res is None else res.ptr, stats_ptr, x.n, hs, ws, x.c, x.ld, ho, wo, r, s, stride,
                   pad, dil, dgrad, ncols, ldw, y.ld, 0 if res is None else res.ld, res_mod, res_div, ldstat, act,
-                  LEAKY_SLOPE, splits, self.prec)
+                  LEAKY_SLOPE, splits, self.prec, b_lo_off)
 
     @staticmethod
     def fwd_splits(M, ncols, K):
@@ -319,7 +341,7 @@ class Graph:
             simple = bias_t is None and act == ACT_NONE and res is None
             raw = y if simple else new_act(x.n, ho, wo, co, self.device)
             self.zero_act(raw)
-            self._igemm(x, wr.wk, co, K, raw, geom=geom, splits=splits)
+            self._igemm(x, wr.operand(), co, K, raw, geom=geom, splits=splits)
             if not simple:
                 self.call("cavp_bn_apply", raw.ptr, raw.ld, self.const_vec(co, 1).data_ptr(),
                           (bias_t if bias_t is not None else self.const_vec(co, 0)).data_ptr(),
@@ -328,7 +350,7 @@ class Graph:
             if want_stats:
                 self.stats_from_tensor(y, stats)
         else:
-            self._igemm(x, wr.wk, co, K, y, geom=geom, y_pre=pre, shift=bias_t, res=res, res_mod=res_mod,
+            self._igemm(x, wr.operand(), co, K, y, geom=geom, y_pre=pre, shift=bias_t, res=res, res_mod=res_mod,
                         res_div=res_div, stats_ptr=0 if stats is None else stats[1],
                         ldstat=0 if stats is None else stats[3], act=act)
 
@@ -375,7 +397,7 @@ class Graph:
                               stride, pad, dil, co, g.ld, wsplits, self.prec)
                     wr.deliver_grad(dwk)
                 if x.needs_grad:
-                    wt = wr.transposed()
+                    wt = wr.operand_t()
                     dx, accumulate = self.grad_target(x)
                     dsplits = self.fwd_splits(x.rows, wr.cin, r * s * co)
                     gs = Act(g.buf, y.n, ho, wo, co, g.off)
@@ -469,12 +491,12 @@ class Graph:
             if splits > 1:
                 raw = new_act(x.n, ho, wo, co, self.device)
                 self.zero_act(raw)
-                self._igemm(x, wr.wk, co, wr.K, raw, geom=(ho, wo, r, s, stride, pad, dil), splits=splits)
+                self._igemm(x, wr.operand(), co, wr.K, raw, geom=(ho, wo, r, s, stride, pad, dil), splits=splits)
                 self.call("cavp_bn_apply", raw.ptr, raw.ld, coeffs[0].data_ptr(), coeffs[1].data_ptr(),
                           0 if res is None else res.ptr, 0 if res is None else res.ld, y.ptr, y.ld, y.rows, co, act,
                           LEAKY_SLOPE)
             else:
-                self._igemm(x, wr.wk, co, wr.K, y, geom=(ho, wo, r, s, stride, pad, dil), scale=coeffs[0],
+                self._igemm(x, wr.operand(), co, wr.K, y, geom=(ho, wo, r, s, stride, pad, dil), scale=coeffs[0],
                             shift=coeffs[1], res=res, act=act)
             return y
         y, stats = self.conv(x, conv_w, stride=stride, pad=pad, dil=dil, want_stats=True, name=name)

@@ -41,7 +41,11 @@ extern "C" {
 int cavp_igemm(const float* x, const float* w, float* y, float* y_pre, const float* scale, const float* shift,
                const float* res, float* stats, int nimg, int hs, int ws, int c, int ldx, int ho, int wo, int r, int s,
                int stride, int pad, int dil, int dgrad, int ncols, int ldw, int ldy, int ldr, int res_mod, int res_div,
-               int ldstat, int act, float slope, int splits, int prec, void* stream);
+               int ldstat, int act, float slope, int splits, int prec, long long b_lo_off, void* stream);
+/* cavp_split_tf32: hi = rn_tf32(w), lo = rn_tf32(w - hi), once per step per weight matrix.  Passing w = hi and
+ * b_lo_off = (lo - hi) > 0 to cavp_igemm makes the kernel fetch the weight operand with TMA (cp.async.bulk.tensor, 128B
+ * swizzle) instead of through the producer warps; b_lo_off = 0 keeps the in-kernel split (operand = activations). */
+int cavp_split_tf32(const float* w, float* hi, float* lo, long long n, void* stream);
 /* cavp_igemm_wgrad: dw[cout][r*s*c] (+)= dy[P][cout]^T * im2col(x)[P][r*s*c]   (weight gradient; P = nimg*ho*wo).
  *   splits > 1 accumulates into a PRE-ZEROED dw. */
 int cavp_igemm_wgrad(const float* dy, const float* x, float* dw, int nimg, int hs, int ws, int c, int ldx, int ho,
