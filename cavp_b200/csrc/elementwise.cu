@@ -80,49 +80,54 @@ __global__ void gather_rows_kernel(const float* __restrict__ src, const long lon
 }
 
 // ------------------------------------------------------------------------------------------------ BatchNorm
-// one warp per channel: reduce the per-(m_tile, quarter) partial sums written by the igemm epilogue (fp64 accumulate)
+// Reduce the per-(m_tile, quarter) partial sums written by the igemm epilogue (fp64 accumulate) and finish the batch
+// statistics.  block = (32 channels, 32 part-lanes): reads are coalesced across channels.
 __global__ void bn_finalize_kernel(const float* __restrict__ partials, int nparts, int ldstat, int C, double count,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
                                    float eps, float* __restrict__ mean_out, float* __restrict__ invstd_out,
                                    float* __restrict__ scale_out, float* __restrict__ shift_out,
                                    double* __restrict__ sums_io, int sums_mode) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= C) return;
+  __shared__ double sh1[32][33], sh2[32][33];
+  const int ch = blockIdx.x * 32 + threadIdx.x;
   double s1 = 0.0, s2 = 0.0;
-  if (sums_mode != 2) {
-    for (int i = lane; i < nparts; i += 32) {
+  if (sums_mode != 2 && ch < C) {
+    for (int i = threadIdx.y; i < nparts; i += 32) {
       const float* pp = partials + static_cast<size_t>(i) * 2 * ldstat;
-      s1 += pp[warp];
-      s2 += pp[ldstat + warp];
+      s1 += pp[ch];
+      s2 += pp[ldstat + ch];
     }
-    s1 = warp_sum_d(s1);
-    s2 = warp_sum_d(s2);
   }
-  if (lane == 0) {
+  sh1[threadIdx.y][threadIdx.x] = s1;
+  sh2[threadIdx.y][threadIdx.x] = s2;
+  __syncthreads();
+  if (threadIdx.y == 0 && ch < C) {
+    for (int j = 1; j < 32; ++j) {
+      s1 += sh1[j][threadIdx.x];
+      s2 += sh2[j][threadIdx.x];
+    }
     if (sums_mode == 1) {  // only export local sums (SyncBatchNorm: all-reduced by the host side, then mode 2)
-      sums_io[warp] = s1;
-      sums_io[C + warp] = s2;
+      sums_io[ch] = s1;
+      sums_io[C + ch] = s2;
       return;
     }
     if (sums_mode == 2) {
-      s1 = sums_io[warp];
-      s2 = sums_io[C + warp];
+      s1 = sums_io[ch];
+      s2 = sums_io[C + ch];
     }
     const double mean = s1 / count;
     double var = s2 / count - mean * mean;
     if (var < 0.0) var = 0.0;
     const float invstd = 1.0f / sqrtf(static_cast<float>(var) + eps);
-    const float g = gamma ? gamma[warp] : 1.f, b = beta ? beta[warp] : 0.f;
-    mean_out[warp] = static_cast<float>(mean);
-    invstd_out[warp] = invstd;
-    scale_out[warp] = g * invstd;
-    shift_out[warp] = b - static_cast<float>(mean) * g * invstd;
+    const float g = gamma ? gamma[ch] : 1.f, b = beta ? beta[ch] : 0.f;
+    mean_out[ch] = static_cast<float>(mean);
+    invstd_out[ch] = invstd;
+    scale_out[ch] = g * invstd;
+    shift_out[ch] = b - static_cast<float>(mean) * g * invstd;
     if (running_mean) {
       const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
-      running_mean[warp] = (1.f - momentum) * running_mean[warp] + momentum * static_cast<float>(mean);
-      running_var[warp] = (1.f - momentum) * running_var[warp] + momentum * static_cast<float>(unbiased);
+      running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * static_cast<float>(mean);
+      running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * static_cast<float>(unbiased);
     }
   }
 }
@@ -532,8 +537,7 @@ extern "C" int cavp_bn_finalize(const float* partials, int nparts, int ldstat, i
                                 const float* beta, float* running_mean, float* running_var, float momentum, float eps,
                                 float* mean_out, float* invstd_out, float* scale_out, float* shift_out, double* sums_io,
                                 int sums_mode, void* stream) {
-  const int threads = 256, warps_per_block = threads / 32;
-  bn_finalize_kernel<<<(C + warps_per_block - 1) / warps_per_block, threads, 0, ST(stream)>>>(
+  bn_finalize_kernel<<<(C + 31) / 32, dim3(32, 32), 0, ST(stream)>>>(
       partials, nparts, ldstat, C, count, gamma, beta, running_mean, running_var, momentum, eps, mean_out, invstd_out,
       scale_out, shift_out, sums_io, sums_mode);
   CAVP_LAUNCH_CHECK();

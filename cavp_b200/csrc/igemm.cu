@@ -113,7 +113,7 @@ extern "C" int cavp_igemm(const float* x, const float* w, float* y, float* y_pre
   if (prec != 1 && prec != 2) return CAVP_ERR_ARG;
   if (stride < 1 || dil < 1 || r < 1 || s < 1) return CAVP_ERR_ARG;
   const long long M = static_cast<long long>(nimg) * ho * wo;
-  if (M <= 0 || M >= (1ll << 31) || static_cast<long long>(nimg) * hs * ws >= (1ll << 31)) return CAVP_ERR_ARG;
+  if (M <= 0 || M >= (1ll << 31) || static_cast<long long>(nimg) * hs * ws * ldx >= (1ll << 31)) return CAVP_ERR_ARG;
   IgemmParams p{};
   p.x = x; p.w = w; p.y = y; p.y_pre = y_pre; p.scale = scale; p.shift = shift; p.res = res; p.stats = stats;
   p.Nimg = nimg; p.Hs = hs; p.Ws = ws; p.C = c; p.ldx = ldx; p.Ho = ho; p.Wo = wo;

@@ -233,14 +233,17 @@ igemm_kernel(const IgemmParams p, const __grid_constant__ CUtensorMap tm_b_hi, c
     }
 
     // ---- operand movers
-    auto load_row_a = [&](int it, float4 (&va)[8]) {
-      const int k = (kb_begin + it) * BK + c * 4;
-      const bool kvalid = k < p.K;
-      uint32_t tap, ci, ky, kx;
-      p.div_c.divmod(static_cast<uint32_t>(kvalid ? k : 0), tap, ci);
-      p.div_s.divmod(tap, ky, kx);
+    // A-gather state: element offsets of this thread's 8 rows for the current filter tap (or -1 = padding / out of
+    // range).  They only change when the k index crosses into the next tap, so the per-k-block work is 8 predicated
+    // 16-byte loads; the tap decomposition and bounds checks run once per tap.
+    int a_off[8];
+    int a_k = 0, a_ci = 0, a_tap = 0;
+    auto a_retap = [&]() {
+      uint32_t ky, kx;
+      p.div_s.divmod(static_cast<uint32_t>(a_tap), ky, kx);
       const int dy = static_cast<int>(ky) * p.dil;
       const int dx = static_cast<int>(kx) * p.dil;
+      const bool kvalid = a_k < p.K;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         int iy, ix;
@@ -261,9 +264,33 @@ igemm_kernel(const IgemmParams p, const __grid_constant__ CUtensorMap tm_b_hi, c
         }
         ok = ok && static_cast<unsigned>(iy) < static_cast<unsigned>(p.Hs) &&
              static_cast<unsigned>(ix) < static_cast<unsigned>(p.Ws);
-        va[i] = ok ? ldg_nc_v4(p.x + static_cast<size_t>(ri.x + iy * p.Ws + ix) * p.ldx + ci)
-                   : make_float4(0.f, 0.f, 0.f, 0.f);
+        a_off[i] = ok ? (ri.x + iy * p.Ws + ix) * p.ldx : -1;
       }
+    };
+    auto a_seek = [&](int it) {  // position on k-block `it` of this CTA's split
+      a_k = (kb_begin + it) * BK + c * 4;
+      uint32_t tap, ci;
+      p.div_c.divmod(static_cast<uint32_t>(a_k < p.K ? a_k : 0), tap, ci);
+      a_tap = static_cast<int>(tap);
+      a_ci = static_cast<int>(ci);
+      a_retap();
+    };
+    auto a_advance = [&]() {  // this group's next k-block is two k-blocks further
+      a_k += 2 * BK;
+      a_ci += 2 * BK;
+      if (a_ci >= p.C || a_k >= p.K) {
+        while (a_ci >= p.C) {
+          a_ci -= p.C;
+          ++a_tap;
+        }
+        a_retap();
+      }
+    };
+    auto load_row_a = [&](float4 (&va)[8]) {
+      const float* base = p.x + a_ci;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        va[i] = a_off[i] >= 0 ? ldg_nc_v4(base + a_off[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
     auto load_row_b = [&](int it, float4 (&vb)[8]) {
       const int k = (kb_begin + it) * BK + c * 4;
@@ -339,7 +366,10 @@ igemm_kernel(const IgemmParams p, const __grid_constant__ CUtensorMap tm_b_hi, c
       float4 va0[8], va1[8];
       auto body = [&](int u, float4 (&cur)[8], float4 (&nxt)[8]) {
         const int it = 2 * u + group;
-        if (it + 2 < nkb) load_row_a(it + 2, nxt);
+        if (it + 2 < nkb) {
+          a_advance();
+          load_row_a(nxt);
+        }
         if (PROMOTE && u >= 2) promote(u - 2);
         if (it < nkb) {
           const int s = it % Cfg::STAGES;
@@ -355,7 +385,10 @@ igemm_kernel(const IgemmParams p, const __grid_constant__ CUtensorMap tm_b_hi, c
           mbar_arrive(&full_bar[s]);
         }
       };
-      if (group < nkb) load_row_a(group, va0);
+      if (group < nkb) {
+        a_seek(group);
+        load_row_a(va0);
+      }
       for (int u = 0; u < npairs; u += 2) {
         body(u, va0, va1);
         if (u + 1 < npairs) body(u + 1, va1, va0);
@@ -370,7 +403,8 @@ igemm_kernel(const IgemmParams p, const __grid_constant__ CUtensorMap tm_b_hi, c
         if (active) {
           mbar_wait(&empty_bar[s], (((it / Cfg::STAGES) & 1) ^ 1));
           if (MODE == MODE_ROW) {
-            load_row_a(it, va);
+            if (u == 0) a_seek(it); else a_advance();
+            load_row_a(va);
             load_row_b(it, vb);
           } else {
             load_wgrad(it, va, vb);

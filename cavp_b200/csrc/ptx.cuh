@@ -153,10 +153,10 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N, int a_mn_ma
 }
 
 // ------------------------------------------------------------------ TF32 split (3xTF32 = fp32-grade products)
+// round-to-nearest (ties away from zero, = cvt.rna.tf32.f32 for finite inputs) in two integer ops; the PTX cvt expands
+// to ~5 SASS instructions because of its NaN/Inf handling, and the split runs 64x per thread per k-block.
 __device__ __forceinline__ float tf32_rn(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t saddr, float a, float b, float c, float d) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
