@@ -247,10 +247,17 @@ def run_ours(args):
         step(True, profile=prof)
         torch.cuda.synchronize()
         agg = {}
-        for name, a, b, fl, nb in prof:
+        rows_ = []
+        for name, a, b, fl, nb, tag in prof:
+            rows_.append((a.elapsed_time(b), name, tag, fl))
             d = agg.setdefault(name, [0.0, 0, 0.0, 0.0])
             d[0] += a.elapsed_time(b); d[1] += 1; d[2] += fl; d[3] += nb
         total_ms = sum(v[0] for v in agg.values())
+        if args.dump_profile:
+            rows_.sort(reverse=True)
+            with open(args.dump_profile, "w") as f:
+                for ms_, name, tag, fl in rows_[:150]:
+                    f.write(f"{ms_:8.3f} ms  {fl / ms_ / 1e9 if ms_ > 0 else 0:7.1f} TF  {name}  {tag}\n")
         ig_ms = agg.get("cavp_igemm", [0, 0, 0, 0])[0] + agg.get("cavp_igemm_wgrad", [0, 0, 0, 0])[0]
         ig_fl = agg.get("cavp_igemm", [0, 0, 0, 0])[2] + agg.get("cavp_igemm_wgrad", [0, 0, 0, 0])[2]
         ig_n = agg.get("cavp_igemm", [0, 0, 0, 0])[1] + agg.get("cavp_igemm_wgrad", [0, 0, 0, 0])[1]
@@ -308,6 +315,7 @@ def main():
     ap.add_argument("--prec", type=int, default=2, help="2 = fp32-parity (3xTF32 + promotion), 1 = plain TF32")
     ap.add_argument("--cpu-batch", type=int, default=4, help="images per CPU reference step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-profile", default=None, help="write the per-launch CUDA-event profile of one step here")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

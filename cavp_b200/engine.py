@@ -157,7 +157,7 @@ class Graph:
         self._const = {}
         self.launches = 0
         self.profile = None  # set to [] to record (name, start_event, end_event, flops, bytes) per kernel launch
-        self._work = (0.0, 0.0)
+        self._work = (0.0, 0.0, "")
 
     # ------------------------------------------------------------------ small helpers
     def call(self, name, *args):
@@ -170,12 +170,12 @@ class Graph:
         _C.call(name, *args, _stream())
         e1.record()
         self.profile.append((name, e0, e1) + self._work)
-        self._work = (0.0, 0.0)
+        self._work = (0.0, 0.0, "")
 
-    def work(self, flops=0.0, nbytes=0.0):
+    def work(self, flops=0.0, nbytes=0.0, tag=""):
         """algorithmic work of the NEXT kernel launch (only used when profiling)."""
         if self.profile is not None:
-            self._work = (float(flops), float(nbytes))
+            self._work = (float(flops), float(nbytes), tag)
 
     def empty(self, *shape, dtype=torch.float32):
         return torch.empty(*shape, device=self.device, dtype=dtype)
@@ -268,7 +268,8 @@ class Graph:
         b_lo_off = 0
         if isinstance(wk, tuple):  # pre-split weight operand -> TMA path
             wk, b_lo_off = wk
-        self.work(flops=2.0 * x.n * ho * wo * ncols * r * s * x.c)
+        self.work(flops=2.0 * x.n * ho * wo * ncols * r * s * x.c,
+                  tag=f"{'dgrad' if dgrad else 'fwd'} M{x.n * ho * wo} N{ncols} K{r * s * x.c} k{r} s{stride} d{dil} splits{splits}")
         self.call("cavp_igemm", x.ptr, wk.data_ptr(), y.ptr, 0 if y_pre is None else y_pre.ptr, _C.ptr(scale),
                   _C.ptr(shift), 0 if res is None else res.ptr, stats_ptr, x.n, hs, ws, x.c, x.ld, ho, wo, r, s, stride,
                   pad, dil, dgrad, ncols, ldw, y.ld, 0 if res is None else res.ld, res_mod, res_div, ldstat, act,
@@ -392,7 +393,7 @@ class Graph:
                     wsplits = self.wgrad_splits(M, co, K)
                     if wsplits > 1:
                         self.call("cavp_zero", dwk.data_ptr(), dwk.numel() * 4)
-                    self.work(flops=2.0 * M * co * K)
+                    self.work(flops=2.0 * M * co * K, tag=f"wgrad P{M} Cout{co} K{K} k{r} s{stride} d{dil} splits{wsplits}")
                     self.call("cavp_igemm_wgrad", g.ptr, x.ptr, dwk.data_ptr(), x.n, x.h, x.w, x.c, x.ld, ho, wo, r, s,
                               stride, pad, dil, co, g.ld, wsplits, self.prec)
                     wr.deliver_grad(dwk)
