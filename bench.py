@@ -165,6 +165,7 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("CAVP_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     torch.manual_seed(666 + rank)  # main_*.py: seed_it(seed + local_rank), seed 666
@@ -242,10 +243,10 @@ def run_ours(args):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
+    prof = []
+    step(True, profile=prof)  # every rank runs it (the step contains the gradient all-reduce)
+    torch.cuda.synchronize()
     if rank == 0:
-        prof = []
-        step(True, profile=prof)
-        torch.cuda.synchronize()
         agg = {}
         rows_ = []
         for name, a, b, fl, nb, tag in prof:
