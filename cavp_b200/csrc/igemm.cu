@@ -1,6 +1,8 @@
 // C-ABI launchers for the tcgen05 implicit-GEMM kernels (igemm.cuh).  See include/cavp_b200.h for the contract.
 #include <cstring>
+#include <cstdlib>
 #include "igemm.cuh"
+#include "igemm_ts.cuh"
 #include "../../include/cavp_b200.h"
 
 namespace cavp {
@@ -50,6 +52,22 @@ static int launch_igemm(const IgemmParams& p, const CUtensorMap& tm_hi, const CU
   return static_cast<int>(cudaGetLastError());
 }
 
+template <int BN, int PREC>
+static int launch_igemm_ts(const IgemmParams& p, const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, cudaStream_t st) {
+  using Cfg = TsCfg<BN, PREC>;
+  auto kern = igemm_ts_kernel<BN, PREC>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    configured = true;
+  }
+  const int m_tiles = (p.M + BM - 1) / BM;
+  dim3 grid(static_cast<unsigned>(m_tiles * p.n_tiles), static_cast<unsigned>(p.splits), 1);
+  kern<<<grid, CTA_THREADS, Cfg::SMEM_BYTES, st>>>(p, tm_hi, tm_lo);
+  return static_cast<int>(cudaGetLastError());
+}
+
 // b_lo_off > 0: the B operand is pre-split ([hi | lo], lo at w + b_lo_off) and is fetched by TMA
 template <int MODE>
 static int dispatch(IgemmParams& p, int prec, long long b_lo_off, cudaStream_t st) {
@@ -64,6 +82,12 @@ static int dispatch(IgemmParams& p, int prec, long long b_lo_off, cudaStream_t s
       if (rc) return rc;
       rc = make_weight_tmap(&tm_lo, p.w + b_lo_off, p.Ncols, p.K, p.ldw, bn);
       if (rc) return rc;
+      static const bool use_ss = getenv("CAVP_IGEMM_TS") == nullptr;  // default: A operand via shared memory (faster); CAVP_IGEMM_TS=1 selects the A-in-TMEM variant
+      if (!use_ss) {
+        if (prec == 2)
+          return bn == 128 ? launch_igemm_ts<128, 2>(p, tm_hi, tm_lo, st) : launch_igemm_ts<64, 2>(p, tm_hi, tm_lo, st);
+        return bn == 128 ? launch_igemm_ts<128, 1>(p, tm_hi, tm_lo, st) : launch_igemm_ts<64, 1>(p, tm_hi, tm_lo, st);
+      }
       if (prec == 2)
         return bn == 128 ? launch_igemm<128, 2, MODE, true>(p, tm_hi, tm_lo, st)
                          : launch_igemm<64, 2, MODE, true>(p, tm_hi, tm_lo, st);

@@ -103,6 +103,119 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane)
   return v[0];
 }
 
+// Epilogue from the fp32 register accumulators of one thread (row = m0 + q*32 + lane, HALF columns starting at
+// n0 + group*HALF): scale/shift/residual/activation, optional pre-activation copy, BN sum / sum-of-squares partials,
+// or raw accumulation (split-K).
+// 32 rows (lanes) x 32 columns (registers) -> global rows, transposed through a warp-private shared-memory scratch so
+// that every store instruction writes four full 128-byte row segments instead of 32 scattered 16-byte pieces.
+__device__ __forceinline__ void store_chunk_coalesced(uint32_t scratch, float* ybase, int ldy, int row0, int M,
+                                                      const float (&v)[32], int lane) {
+  constexpr int LDS_ = 36;  // floats per scratch row (16-byte aligned, conflict-free for quarter-warp accesses)
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 32; j += 4)
+    st_shared_v4(scratch + static_cast<uint32_t>((lane * LDS_ + j) * 4), v[j], v[j + 1], v[j + 2], v[j + 3]);
+  __syncwarp();
+  const int c4 = lane & 7, rsub = lane >> 3;
+#pragma unroll
+  for (int rr = 0; rr < 8; ++rr) {
+    const int r = rr * 4 + rsub;
+    float4 t;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
+                 : "r"(scratch + static_cast<uint32_t>((r * LDS_ + c4 * 4) * 4)));
+    if (row0 + r < M) *reinterpret_cast<float4*>(ybase + static_cast<size_t>(r) * ldy + c4 * 4) = t;
+  }
+}
+
+template <int HALF>
+__device__ __forceinline__ void igemm_epilogue(const IgemmParams& p, float (&acc)[HALF], int m0, int n0, int m_tile,
+                                               int group, int q, int lane, uint32_t scratch) {
+  const int row = m0 + q * 32 + lane;
+  const int row0 = m0 + q * 32;
+  const bool row_ok = row < p.M;
+  const bool vec_ok = ((p.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
+  size_t res_row = 0;
+  if (p.res) {
+    int rr_ = p.res_div > 1 ? row / p.res_div : row;
+    if (p.res_mod > 0) rr_ %= p.res_mod;
+    res_row = static_cast<size_t>(rr_);
+  }
+#pragma unroll
+  for (int cgrp = 0; cgrp < HALF / 32; ++cgrp) {
+    const int col0 = n0 + group * HALF + cgrp * 32;
+    if (col0 < p.Ncols) {
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = acc[cgrp * 32 + j];
+      float* yrow = p.y + static_cast<size_t>(row) * p.ldy + col0;
+      if (p.splits > 1) {
+        if (row_ok) {
+          if (vec_ok && col0 + 32 <= p.Ncols) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) red_add_v4(yrow + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.Ncols) atomicAdd(yrow + j, v[j]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = col0 + j;
+          if (col < p.Ncols) {
+            float t = v[j];
+            if (p.scale) t *= __ldg(p.scale + col);
+            if (p.shift) t += __ldg(p.shift + col);
+            if (p.res && row_ok) t += __ldg(p.res + res_row * p.ldr + col);
+            v[j] = t;
+          } else {
+            v[j] = 0.f;
+          }
+        }
+        const bool full_chunk = vec_ok && col0 + 32 <= p.Ncols;
+        if (p.y_pre) {
+          if (full_chunk && (reinterpret_cast<uintptr_t>(p.y_pre) & 15) == 0) {
+            store_chunk_coalesced(scratch, p.y_pre + static_cast<size_t>(row0) * p.ldy + col0, p.ldy, row0, p.M, v, lane);
+          } else if (row_ok) {
+            float* prow = p.y_pre + static_cast<size_t>(row) * p.ldy + col0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.Ncols) prow[j] = v[j];
+          }
+        }
+        if (p.act != ACT_NONE) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act, p.slope);
+        }
+        if (full_chunk) {
+          store_chunk_coalesced(scratch, p.y + static_cast<size_t>(row0) * p.ldy + col0, p.ldy, row0, p.M, v, lane);
+        } else if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.Ncols) yrow[j] = v[j];
+        }
+        if (p.stats) {
+          float sq[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (!row_ok) v[j] = 0.f;
+            sq[j] = v[j] * v[j];
+          }
+          const float s1 = warp_transpose_reduce(v, lane);
+          const float s2 = warp_transpose_reduce(sq, lane);
+          if (col0 + lane < p.Ncols) {
+            float* st = p.stats + static_cast<size_t>(m_tile * 4 + q) * 2 * p.ldstat;
+            st[col0 + lane] = s1;
+            st[p.ldstat + col0 + lane] = s2;
+          }
+        }
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 template <int BN, int PREC, int MODE, bool BTMA>
 __global__ void __launch_bounds__(CTA_THREADS, 1)
@@ -429,88 +542,7 @@ igemm_kernel(const IgemmParams p, const __grid_constant__ CUtensorMap tm_b_hi, c
       promote(0);
     }
 
-    // ===================================================== epilogue from registers
-    const int row = m0 + q * 32 + lane;
-    const bool row_ok = row < p.M;
-    const bool vec_ok = ((p.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
-    size_t res_row = 0;
-    if (p.res) {
-      int rr_ = p.res_div > 1 ? row / p.res_div : row;
-      if (p.res_mod > 0) rr_ %= p.res_mod;
-      res_row = static_cast<size_t>(rr_);
-    }
-#pragma unroll
-    for (int cgrp = 0; cgrp < HALF / 32; ++cgrp) {
-      const int col0 = n0 + group * HALF + cgrp * 32;
-      if (col0 < p.Ncols) {
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = acc[cgrp * 32 + j];
-        float* yrow = p.y + static_cast<size_t>(row) * p.ldy + col0;
-        if (p.splits > 1) {
-          if (row_ok) {
-            if (vec_ok && col0 + 32 <= p.Ncols) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) red_add_v4(yrow + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.Ncols) atomicAdd(yrow + j, v[j]);
-            }
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int col = col0 + j;
-            if (col < p.Ncols) {
-              float t = v[j];
-              if (p.scale) t *= __ldg(p.scale + col);
-              if (p.shift) t += __ldg(p.shift + col);
-              if (p.res && row_ok) t += __ldg(p.res + res_row * p.ldr + col);
-              v[j] = t;
-            } else {
-              v[j] = 0.f;
-            }
-          }
-          if (p.y_pre && row_ok) {
-            float* prow = p.y_pre + static_cast<size_t>(row) * p.ldy + col0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.Ncols) prow[j] = v[j];
-          }
-          if (p.act != ACT_NONE) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act, p.slope);
-          }
-          if (row_ok) {
-            if (vec_ok && col0 + 32 <= p.Ncols) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(yrow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.Ncols) yrow[j] = v[j];
-            }
-          }
-          if (p.stats) {
-            float sq[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (!row_ok) v[j] = 0.f;
-              sq[j] = v[j] * v[j];
-            }
-            const float s1 = warp_transpose_reduce(v, lane);
-            const float s2 = warp_transpose_reduce(sq, lane);
-            if (col0 + lane < p.Ncols) {
-              float* st = p.stats + static_cast<size_t>(m_tile * 4 + q) * 2 * p.ldstat;
-              st[col0 + lane] = s1;
-              st[p.ldstat + col0 + lane] = s2;
-            }
-          }
-        }
-      }
-    }
+    igemm_epilogue<HALF>(p, acc, m0, n0, m_tile, group, q, lane, smem_base + static_cast<uint32_t>(warp * 4608));
   } else {
     // ===================================================== MMA issuer (warp 8, one thread)
     if (lane == 0) {
