@@ -323,7 +323,7 @@ igemm_kernel(const IgemmParams p, const __grid_constant__ CUtensorMap tm_b_hi, c
 
     // ---- per-thread operand addressing
     // MODE_ROW  : chunk column c (16 B) of the 128-byte k-row; rows r0 + 16 i
-    // MODE_WGRAD: chunk cc (16 B) along MN (atom = cc>>3); k-rows (pixels) rr + 4 i
+    // MODE_WGRAD: chunk cc (16 B) along MN (atom = cc>>3); k-rows (pixels) rr*8 + i
     const int c = gtid & 7;
     const int r0 = gtid >> 3;
     const uint32_t swz = static_cast<uint32_t>((c ^ (r0 & 7)) << 4);
@@ -416,27 +416,33 @@ igemm_kernel(const IgemmParams p, const __grid_constant__ CUtensorMap tm_b_hi, c
       }
     };
     auto load_wgrad = [&](int it, float4 (&va)[8], float4 (&vb)[8]) {
-      const int pix0 = (kb_begin + it) * BK;
+      // this warp's k-rows are the 8 consecutive pixels rr*8 .. rr*8+7 of the k-block: decode the first one, then walk
+      // (ox, oy, image) incrementally instead of 8 divmod pairs
+      const int pixb = (kb_begin + it) * BK + rr * 8;
+      uint32_t n, rem, oy, ox;
+      p.div_howo.divmod(static_cast<uint32_t>(pixb < p.red_len ? pixb : 0), n, rem);
+      p.div_wo.divmod(rem, oy, ox);
+      int base = static_cast<int>(n) * p.Hs * p.Ws;
+      int y = static_cast<int>(oy) * p.stride + wg_dy, x = static_cast<int>(ox) * p.stride + wg_dx;
+      const int x_wrap = p.Wo * p.stride + wg_dx, y_wrap = p.Ho * p.stride + wg_dy;
+      const float* dyp = p.w + static_cast<size_t>(pixb) * p.ldw + wg_co;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int pix = pix0 + rr + 4 * i;
-        const bool pok = pix < p.red_len;
-        va[i] = (pok && wg_co_ok) ? ldg_nc_v4(p.w + static_cast<size_t>(pix) * p.ldw + wg_co)
-                                  : make_float4(0.f, 0.f, 0.f, 0.f);
-        bool ok = pok && wg_j_ok;
-        uint32_t n = 0, rem, oy = 0, ox = 0;
-        if (ok) {
-          p.div_howo.divmod(static_cast<uint32_t>(pix), n, rem);
-          p.div_wo.divmod(rem, oy, ox);
-        }
-        const int iy = static_cast<int>(oy) * p.stride + wg_dy;
-        const int ix = static_cast<int>(ox) * p.stride + wg_dx;
-        ok = ok && static_cast<unsigned>(iy) < static_cast<unsigned>(p.Hs) &&
-             static_cast<unsigned>(ix) < static_cast<unsigned>(p.Ws);
-        vb[i] = ok ? ldg_nc_v4(p.x +
-                               (static_cast<size_t>(n) * p.Hs * p.Ws + static_cast<size_t>(iy) * p.Ws + ix) * p.ldx +
-                               wg_ci)
+        const bool pok = pixb + i < p.red_len;
+        va[i] = (pok && wg_co_ok) ? ldg_nc_v4(dyp + static_cast<size_t>(i) * p.ldw) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool ok = pok && wg_j_ok && static_cast<unsigned>(y) < static_cast<unsigned>(p.Hs) &&
+                        static_cast<unsigned>(x) < static_cast<unsigned>(p.Ws);
+        vb[i] = ok ? ldg_nc_v4(p.x + static_cast<size_t>(base + y * p.Ws + x) * p.ldx + wg_ci)
                    : make_float4(0.f, 0.f, 0.f, 0.f);
+        x += p.stride;
+        if (x == x_wrap) {
+          x = wg_dx;
+          y += p.stride;
+          if (y == y_wrap) {
+            y = wg_dy;
+            base += p.Hs * p.Ws;
+          }
+        }
       }
     };
     auto store_row_a = [&](int s, const float4 (&va)[8]) {
@@ -464,7 +470,7 @@ igemm_kernel(const IgemmParams p, const __grid_constant__ CUtensorMap tm_b_hi, c
       const int c16 = cc & 7;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int r = rr + 4 * i;
+        const int r = rr * 8 + i;
         const uint32_t off = atom_off + static_cast<uint32_t>(r * 128) +
                              static_cast<uint32_t>((((c16 >> 1) ^ (r & 3)) << 5) | ((c16 & 1) << 4));
         store_split<PREC>(a_hi + off, a_lo + off, va[i]);
