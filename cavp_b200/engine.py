@@ -157,17 +157,22 @@ class Graph:
         self._const = {}
         self.launches = 0
         self.profile = None  # set to [] to record (name, start_event, end_event, flops, bytes) per kernel launch
+        self._stream = torch.cuda.current_stream(device).cuda_stream if torch.cuda.is_available() else 0
+        _C.lib()
+        self._fns = _C._fns
         self._work = (0.0, 0.0, "")
 
     # ------------------------------------------------------------------ small helpers
     def call(self, name, *args):
         self.launches += 1
         if self.profile is None:
-            _C.call(name, *args, _stream())
+            rc = self._fns[name](*args, self._stream)
+            if rc != 0:
+                raise _C.CavpError(f"{name} failed with status {rc}")
             return
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        _C.call(name, *args, _stream())
+        _C.call(name, *args, self._stream)
         e1.record()
         self.profile.append((name, e0, e1) + self._work)
         self._work = (0.0, 0.0, "")
