@@ -14,6 +14,7 @@ GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
     config.addinivalue_line("markers", "reference: needs /root/reference mounted (build container only)")
+    config.addinivalue_line("markers", "gpu2: needs torchrun with 2 GPUs (not part of the default -m gpu run)")
 
 
 def pytest_collection_modifyitems(config, items):
