@@ -124,9 +124,14 @@ constexpr int GATE_MAX_V4 = 3;   // C <= 384
 constexpr int GATE_MAX_REP = 2;  // rows sharing one q row
 constexpr int GATE_HEADS = 4;
 
-__global__ void gate_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
-                                float* __restrict__ x, float* __restrict__ attn, int Bq, int rep, int N, int C4, int D4,
-                                float scale) {
+// Lane mapping: head h <-> lanes 8h..8h+7 (4 heads x 8 lanes); a lane owns float4 chunks l8, l8+8, l8+16 of its head's
+// D/4 chunks, so a per-head dot product is a 3-step shuffle reduction inside the quarter-warp, and every load / store
+// instruction touches four contiguous 128-byte segments.  Two tokens are processed per iteration to keep more loads
+// in flight (the kernel is a pure HBM stream: 1 read + rep writes of N*C floats).
+__global__ void __launch_bounds__(256) gate_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                                                        const float* __restrict__ v, float* __restrict__ x,
+                                                        float* __restrict__ attn, int Bq, int rep, int N, int C4,
+                                                        int D4, float scale) {
   extern __shared__ float4 kv_sh[];  // [rep][2][C4]
   const int b = blockIdx.y;
   for (int i = threadIdx.x; i < rep * 2 * C4; i += blockDim.x) {
@@ -136,57 +141,62 @@ __global__ void gate_fwd_kernel(const float* __restrict__ q, const float* __rest
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int n = blockIdx.x * nw + warp; n < N; n += gridDim.x * nw) {
-    const float4* qr = reinterpret_cast<const float4*>(q + (static_cast<long long>(b) * N + n) * C4 * 4);
-    float4 qv[GATE_MAX_V4];
+  const int h = lane >> 3, l8 = lane & 7;
+  int fidx[GATE_MAX_V4];
+  bool fok[GATE_MAX_V4];
 #pragma unroll
-    for (int kk = 0; kk < GATE_MAX_V4; ++kk) {
-      const int f = lane + 32 * kk;
-      if (f < C4) qv[kk] = qr[f];
+  for (int j = 0; j < GATE_MAX_V4; ++j) {
+    fok[j] = l8 + 8 * j < D4;
+    fidx[j] = h * D4 + (fok[j] ? l8 + 8 * j : 0);
+  }
+  constexpr int TOK = 2;
+  for (int n0 = (blockIdx.x * nw + warp) * TOK; n0 < N; n0 += gridDim.x * nw * TOK) {
+    float4 qv[TOK][GATE_MAX_V4];
+#pragma unroll
+    for (int t = 0; t < TOK; ++t) {
+      const int n = n0 + t < N ? n0 + t : N - 1;
+      const float4* qr = reinterpret_cast<const float4*>(q + (static_cast<long long>(b) * N + n) * C4 * 4);
+#pragma unroll
+      for (int j = 0; j < GATE_MAX_V4; ++j) qv[t][j] = fok[j] ? __ldg(qr + fidx[j]) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     for (int rp = 0; rp < rep; ++rp) {
       const float4* ks = kv_sh + rp * 2 * C4;
       const float4* vs = ks + C4;
-      float part[GATE_HEADS] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int kk = 0; kk < GATE_MAX_V4; ++kk) {
-        const int f = lane + 32 * kk;
-        if (f < C4) {
-          const float4 kf = ks[f];
-          const float d = qv[kk].x * kf.x + qv[kk].y * kf.y + qv[kk].z * kf.z + qv[kk].w * kf.w;
-          const int h = f / D4;
-#pragma unroll
-          for (int hh = 0; hh < GATE_HEADS; ++hh) part[hh] += (h == hh) ? d : 0.f;
-        }
-      }
-      float a[GATE_HEADS];
-#pragma unroll
-      for (int hh = 0; hh < GATE_HEADS; ++hh) a[hh] = 1.f / (1.f + expf(-warp_sum(part[hh]) * scale));
       const long long r = b + static_cast<long long>(rp) * Bq;
-      float4* xr = reinterpret_cast<float4*>(x + (r * N + n) * C4 * 4);
+      float4 kf[GATE_MAX_V4], vf[GATE_MAX_V4];
 #pragma unroll
-      for (int kk = 0; kk < GATE_MAX_V4; ++kk) {
-        const int f = lane + 32 * kk;
-        if (f < C4) {
-          const int h = f / D4;
-          const float ah = h == 0 ? a[0] : (h == 1 ? a[1] : (h == 2 ? a[2] : a[3]));
-          const float4 vf = vs[f];
-          xr[f] = make_float4(ah * vf.x, ah * vf.y, ah * vf.z, ah * vf.w);
-        }
+      for (int j = 0; j < GATE_MAX_V4; ++j) {
+        kf[j] = ks[fidx[j]];
+        vf[j] = vs[fidx[j]];
       }
-      if (lane < GATE_HEADS) {
-        const float ah = lane == 0 ? a[0] : (lane == 1 ? a[1] : (lane == 2 ? a[2] : a[3]));
-        attn[(r * GATE_HEADS + lane) * N + n] = ah;
+#pragma unroll
+      for (int t = 0; t < TOK; ++t) {
+        float d = 0.f;
+#pragma unroll
+        for (int j = 0; j < GATE_MAX_V4; ++j)
+          if (fok[j]) d += qv[t][j].x * kf[j].x + qv[t][j].y * kf[j].y + qv[t][j].z * kf[j].z + qv[t][j].w * kf[j].w;
+        d += __shfl_xor_sync(0xffffffffu, d, 4);
+        d += __shfl_xor_sync(0xffffffffu, d, 2);
+        d += __shfl_xor_sync(0xffffffffu, d, 1);
+        const float a = 1.f / (1.f + expf(-d * scale));
+        if (n0 + t < N) {
+          float4* xr = reinterpret_cast<float4*>(x + (r * N + n0 + t) * C4 * 4);
+#pragma unroll
+          for (int j = 0; j < GATE_MAX_V4; ++j)
+            if (fok[j]) xr[fidx[j]] = make_float4(a * vf[j].x, a * vf[j].y, a * vf[j].z, a * vf[j].w);
+          if (l8 == 0) attn[(r * GATE_HEADS + h) * N + n0 + t] = a;
+        }
       }
     }
   }
 }
 
 // backward: dq (summed over the rows that share q), dk / dv accumulated with atomics (pre-zeroed [rows][C]).
-__global__ void gate_bwd_kernel(const float* __restrict__ dx, const float* __restrict__ q, const float* __restrict__ k,
-                                const float* __restrict__ v, const float* __restrict__ attn, float* __restrict__ dq,
-                                float* __restrict__ dk, float* __restrict__ dv, int Bq, int rep, int N, int C4, int D4,
-                                float scale) {
+__global__ void __launch_bounds__(256, 2) gate_bwd_kernel(const float* __restrict__ dx, const float* __restrict__ q,
+                                                        const float* __restrict__ k, const float* __restrict__ v,
+                                                        const float* __restrict__ attn, float* __restrict__ dq,
+                                                        float* __restrict__ dk, float* __restrict__ dv, int Bq, int rep,
+                                                        int N, int C4, int D4, float scale) {
   extern __shared__ float4 kv_sh[];  // [rep][2][C4] k,v  then [rep][2][C4] block accumulators (as floats)
   float* acc_sh = reinterpret_cast<float*>(kv_sh + rep * 2 * C4);
   const int b = blockIdx.y;
@@ -198,20 +208,36 @@ __global__ void gate_bwd_kernel(const float* __restrict__ dx, const float* __res
   for (int i = threadIdx.x; i < rep * 2 * C4 * 4; i += blockDim.x) acc_sh[i] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int h = lane >> 3, l8 = lane & 7;  // same quarter-warp-per-head mapping as the forward kernel
+  int fidx[GATE_MAX_V4];
+  bool fok[GATE_MAX_V4];
+#pragma unroll
+  for (int j = 0; j < GATE_MAX_V4; ++j) {
+    fok[j] = l8 + 8 * j < D4;
+    fidx[j] = h * D4 + (fok[j] ? l8 + 8 * j : 0);
+  }
   float4 dk_acc[GATE_MAX_REP][GATE_MAX_V4], dv_acc[GATE_MAX_REP][GATE_MAX_V4];
 #pragma unroll
   for (int rp = 0; rp < GATE_MAX_REP; ++rp)
 #pragma unroll
-    for (int kk = 0; kk < GATE_MAX_V4; ++kk) dk_acc[rp][kk] = dv_acc[rp][kk] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < GATE_MAX_V4; ++j) dk_acc[rp][j] = dv_acc[rp][j] = make_float4(0.f, 0.f, 0.f, 0.f);
 
   for (int n = blockIdx.x * nw + warp; n < N; n += gridDim.x * nw) {
     const float4* qr = reinterpret_cast<const float4*>(q + (static_cast<long long>(b) * N + n) * C4 * 4);
-    float4 qv[GATE_MAX_V4], dqv[GATE_MAX_V4];
+    float4 qv[GATE_MAX_V4], dqv[GATE_MAX_V4], g[GATE_MAX_REP][GATE_MAX_V4];
 #pragma unroll
-    for (int kk = 0; kk < GATE_MAX_V4; ++kk) {
-      const int f = lane + 32 * kk;
-      if (f < C4) qv[kk] = qr[f];
-      dqv[kk] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < GATE_MAX_V4; ++j) {
+      qv[j] = fok[j] ? __ldg(qr + fidx[j]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      dqv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int rp = 0; rp < GATE_MAX_REP; ++rp) {
+      if (rp < rep) {
+        const long long r = b + static_cast<long long>(rp) * Bq;
+        const float4* gr = reinterpret_cast<const float4*>(dx + (r * N + n) * C4 * 4);
+#pragma unroll
+        for (int j = 0; j < GATE_MAX_V4; ++j) g[rp][j] = fok[j] ? __ldg(gr + fidx[j]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
 #pragma unroll
     for (int rp = 0; rp < GATE_MAX_REP; ++rp) {
@@ -219,65 +245,46 @@ __global__ void gate_bwd_kernel(const float* __restrict__ dx, const float* __res
         const float4* ks = kv_sh + rp * 2 * C4;
         const float4* vs = ks + C4;
         const long long r = b + static_cast<long long>(rp) * Bq;
-        const float4* gr = reinterpret_cast<const float4*>(dx + (r * N + n) * C4 * 4);
-        float4 g[GATE_MAX_V4];
-        float part[GATE_HEADS] = {0.f, 0.f, 0.f, 0.f};
+        float d = 0.f;
 #pragma unroll
-        for (int kk = 0; kk < GATE_MAX_V4; ++kk) {
-          const int f = lane + 32 * kk;
-          if (f < C4) {
-            g[kk] = gr[f];
-            const float4 vf = vs[f];
-            const float d = g[kk].x * vf.x + g[kk].y * vf.y + g[kk].z * vf.z + g[kk].w * vf.w;
-            const int h = f / D4;
-#pragma unroll
-            for (int hh = 0; hh < GATE_HEADS; ++hh) part[hh] += (h == hh) ? d : 0.f;
-          }
+        for (int j = 0; j < GATE_MAX_V4; ++j) {
+          const float4 vf = vs[fidx[j]];
+          d += g[rp][j].x * vf.x + g[rp][j].y * vf.y + g[rp][j].z * vf.z + g[rp][j].w * vf.w;
         }
-        float a[GATE_HEADS], ds[GATE_HEADS];
+        d += __shfl_xor_sync(0xffffffffu, d, 4);
+        d += __shfl_xor_sync(0xffffffffu, d, 2);
+        d += __shfl_xor_sync(0xffffffffu, d, 1);
+        const float a = attn[(r * GATE_HEADS + h) * N + n];
+        const float ds = d * a * (1.f - a) * scale;
 #pragma unroll
-        for (int hh = 0; hh < GATE_HEADS; ++hh) {
-          a[hh] = attn[(r * GATE_HEADS + hh) * N + n];
-          ds[hh] = warp_sum(part[hh]) * a[hh] * (1.f - a[hh]) * scale;
-        }
-#pragma unroll
-        for (int kk = 0; kk < GATE_MAX_V4; ++kk) {
-          const int f = lane + 32 * kk;
-          if (f < C4) {
-            const int h = f / D4;
-            const float dsh = h == 0 ? ds[0] : (h == 1 ? ds[1] : (h == 2 ? ds[2] : ds[3]));
-            const float ah = h == 0 ? a[0] : (h == 1 ? a[1] : (h == 2 ? a[2] : a[3]));
-            const float4 kf = ks[f];
-            dqv[kk].x += dsh * kf.x; dqv[kk].y += dsh * kf.y; dqv[kk].z += dsh * kf.z; dqv[kk].w += dsh * kf.w;
-            dk_acc[rp][kk].x += dsh * qv[kk].x; dk_acc[rp][kk].y += dsh * qv[kk].y;
-            dk_acc[rp][kk].z += dsh * qv[kk].z; dk_acc[rp][kk].w += dsh * qv[kk].w;
-            dv_acc[rp][kk].x += ah * g[kk].x; dv_acc[rp][kk].y += ah * g[kk].y;
-            dv_acc[rp][kk].z += ah * g[kk].z; dv_acc[rp][kk].w += ah * g[kk].w;
-          }
+        for (int j = 0; j < GATE_MAX_V4; ++j) {
+          const float4 kf = ks[fidx[j]];
+          dqv[j].x += ds * kf.x; dqv[j].y += ds * kf.y; dqv[j].z += ds * kf.z; dqv[j].w += ds * kf.w;
+          dk_acc[rp][j].x += ds * qv[j].x; dk_acc[rp][j].y += ds * qv[j].y;
+          dk_acc[rp][j].z += ds * qv[j].z; dk_acc[rp][j].w += ds * qv[j].w;
+          dv_acc[rp][j].x += a * g[rp][j].x; dv_acc[rp][j].y += a * g[rp][j].y;
+          dv_acc[rp][j].z += a * g[rp][j].z; dv_acc[rp][j].w += a * g[rp][j].w;
         }
       }
     }
     float4* dqr = reinterpret_cast<float4*>(dq + (static_cast<long long>(b) * N + n) * C4 * 4);
 #pragma unroll
-    for (int kk = 0; kk < GATE_MAX_V4; ++kk) {
-      const int f = lane + 32 * kk;
-      if (f < C4) dqr[f] = dqv[kk];
-    }
+    for (int j = 0; j < GATE_MAX_V4; ++j)
+      if (fok[j]) dqr[fidx[j]] = dqv[j];
   }
   // block reduce of dk/dv through shared memory, then one atomic per element per block
 #pragma unroll
   for (int rp = 0; rp < GATE_MAX_REP; ++rp) {
     if (rp < rep) {
 #pragma unroll
-      for (int kk = 0; kk < GATE_MAX_V4; ++kk) {
-        const int f = lane + 32 * kk;
-        if (f < C4) {
-          float* ak = acc_sh + ((rp * 2 + 0) * C4 + f) * 4;
-          float* av = acc_sh + ((rp * 2 + 1) * C4 + f) * 4;
-          atomicAdd(ak + 0, dk_acc[rp][kk].x); atomicAdd(ak + 1, dk_acc[rp][kk].y);
-          atomicAdd(ak + 2, dk_acc[rp][kk].z); atomicAdd(ak + 3, dk_acc[rp][kk].w);
-          atomicAdd(av + 0, dv_acc[rp][kk].x); atomicAdd(av + 1, dv_acc[rp][kk].y);
-          atomicAdd(av + 2, dv_acc[rp][kk].z); atomicAdd(av + 3, dv_acc[rp][kk].w);
+      for (int j = 0; j < GATE_MAX_V4; ++j) {
+        if (fok[j]) {
+          float* ak = acc_sh + ((rp * 2 + 0) * C4 + fidx[j]) * 4;
+          float* av = acc_sh + ((rp * 2 + 1) * C4 + fidx[j]) * 4;
+          atomicAdd(ak + 0, dk_acc[rp][j].x); atomicAdd(ak + 1, dk_acc[rp][j].y);
+          atomicAdd(ak + 2, dk_acc[rp][j].z); atomicAdd(ak + 3, dk_acc[rp][j].w);
+          atomicAdd(av + 0, dv_acc[rp][j].x); atomicAdd(av + 1, dv_acc[rp][j].y);
+          atomicAdd(av + 2, dv_acc[rp][j].z); atomicAdd(av + 3, dv_acc[rp][j].w);
         }
       }
     }
@@ -332,7 +339,8 @@ extern "C" int cavp_gate_fwd(const float* q, const float* k, const float* v, flo
   if (heads != GATE_HEADS || (C & 3) || (C / heads) % 4 || C / 4 > 32 * GATE_MAX_V4 || rep < 1 || rep > GATE_MAX_REP)
     return CAVP_ERR_ARG;
   const int C4 = C / 4, D4 = C / heads / 4;
-  int gx = (N + 7) / 8;
+  if ((C / heads / 4 + 7) / 8 > GATE_MAX_V4) return CAVP_ERR_ARG;
+  int gx = (N + 15) / 16;
   const int cap = (NUM_SMS * 8 + Bq - 1) / Bq;
   if (gx > cap) gx = cap;
   dim3 grid(gx, Bq);
