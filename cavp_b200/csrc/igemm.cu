@@ -3,6 +3,7 @@
 #include <cstdlib>
 #include "igemm.cuh"
 #include "igemm_ts.cuh"
+#include "igemm_ws.cuh"
 #include "../../include/cavp_b200.h"
 
 namespace cavp {
@@ -68,6 +69,23 @@ static int launch_igemm_ts(const IgemmParams& p, const CUtensorMap& tm_hi, const
   return static_cast<int>(cudaGetLastError());
 }
 
+template <int BN, int PREC>
+static int launch_igemm_ws(const IgemmParams& p, const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, cudaStream_t st) {
+  using Cfg = WsCfg<BN, PREC>;
+  auto kern = igemm_ws_kernel<BN, PREC>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    configured = true;
+  }
+  const int m_tiles = (p.M + BM - 1) / BM;
+  const int total_work = m_tiles * p.n_tiles * p.splits;
+  const int grid = total_work < 148 ? total_work : 148;
+  kern<<<grid, WS_THREADS, Cfg::SMEM_BYTES, st>>>(p, tm_hi, tm_lo, total_work);
+  return static_cast<int>(cudaGetLastError());
+}
+
 // b_lo_off > 0: the B operand is pre-split ([hi | lo], lo at w + b_lo_off) and is fetched by TMA
 template <int MODE>
 static int dispatch(IgemmParams& p, int prec, long long b_lo_off, cudaStream_t st) {
@@ -82,6 +100,16 @@ static int dispatch(IgemmParams& p, int prec, long long b_lo_off, cudaStream_t s
       if (rc) return rc;
       rc = make_weight_tmap(&tm_lo, p.w + b_lo_off, p.Ncols, p.K, p.ldw, bn);
       if (rc) return rc;
+      // schedule selection: the persistent warp-specialised kernel wins at PREC=1 (+20 %) but not at
+      // PREC=2, where the tile kernel is bound by shared-memory bandwidth rather than by fill/drain.  CAVP_IGEMM_WS=1/0
+      // forces it on/off.
+      static const char* ws_env = getenv("CAVP_IGEMM_WS");
+      const bool use_ws = ws_env ? (ws_env[0] != '0') : (prec == 1);
+      if (use_ws) {
+        if (prec == 2)
+          return bn == 128 ? launch_igemm_ws<128, 2>(p, tm_hi, tm_lo, st) : launch_igemm_ws<64, 2>(p, tm_hi, tm_lo, st);
+        return bn == 128 ? launch_igemm_ws<128, 1>(p, tm_hi, tm_lo, st) : launch_igemm_ws<64, 1>(p, tm_hi, tm_lo, st);
+      }
       static const bool use_ss = getenv("CAVP_IGEMM_TS") == nullptr;  // default: A operand via shared memory (faster); CAVP_IGEMM_TS=1 selects the A-in-TMEM variant
       if (!use_ss) {
         if (prec == 2)

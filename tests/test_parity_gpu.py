@@ -153,3 +153,83 @@ def test_module_autograd_path_equals_train_step():
             a, b = p2.grad.double().flatten(), p1.grad.double().flatten()
             assert float((a - b).norm() / b.norm().clamp_min(1e-30)) < GRAD_SAMPLE_L2_TOL, k
             assert abs(float(a.norm() - b.norm())) / float(b.norm().clamp_min(1e-30)) < GRAD_NORM_TOL, k
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# edge cases against the oracle on the same seeded inputs (the reference itself has no tests: SURVEY.md section 4)
+# ---------------------------------------------------------------------------------------------------------------
+def _oracle_train(cfg, batch, spl, seed):
+    from oracle import cavp_oracle as O
+    sd = schema.seeded_state(cfg["nc"], cfg["audio"], cfg["in_plane"], seed=0, requires_grad=True)
+    torch.manual_seed(seed)
+    return O.train_step_losses(sd, batch, spl, dilation_flags=cfg["dilation"], audio_kind=cfg["audio"],
+                               max_views=cfg["max_views"])
+
+
+@pytest.mark.parametrize("cfg", [
+    # minimum legal train batch, binary AVSBench-object classes, non-square input
+    dict(B=2, H=96, W=128, nc=2, dilation=(False, False, False), audio="vgg", in_plane=1, frames=96, max_views=16),
+    # odd feature-map sizes: 72x104 -> stride-4 map 18x26, stride-16 maps 5x7 (ASPP dilations mostly in the padding)
+    dict(B=3, H=72, W=104, nc=22, dilation=(False, True, True), audio="vgg", in_plane=1, frames=96, max_views=32),
+])
+def test_train_step_edge_shapes_match_oracle(cfg):
+    from cavp_b200.trainer import shuffled_labels, train_step
+    model = build_model(cfg).train()
+    batch = batch_for(cfg)
+    spl = shuffled_labels(batch["pix_label"], batch["img_label"], batch["shuffle_idx"])
+    torch.manual_seed(77)
+    res = train_step(model, batch["image"].cuda(), batch["audio"].cuda(), batch["pix_label"], spl,
+                     max_views=cfg["max_views"], keep_outputs=True)
+    l_ce, l_ctr, out_cat, ctr_cat, pack, newbuf = _oracle_train(cfg, batch, spl, 77)
+    errs = dict(pred=rel_err(res.out_pred, out_cat), fusion=rel_err(res.out_fusion, ctr_cat),
+                attn=rel_err(res.attn_v, pack["attn_v"]), l_ce=abs(float(res.l_ce) - float(l_ce)) / abs(float(l_ce)))
+    if float(l_ctr) != 0.0:
+        errs["l_ctr"] = abs(float(res.l_ctr) - float(l_ctr)) / abs(float(l_ctr))
+    else:
+        assert float(res.l_ctr) == 0.0  # no class reached max_views pixels: reference returns tensor([0.])
+    print(cfg["H"], cfg["W"], {k: "%.2e" % v for k, v in errs.items()})
+    # Tiny batches / 5x7 feature maps make the batch-stat BN chain even more ill-conditioned than the golden fixtures
+    # (observed 5e-4 .. 1e-3 against the fp32 oracle, run-to-run spread from atomics included), so the train-mode
+    # edge cases use 3e-3; the same shapes are checked at 1e-4 in eval mode below, where nothing amplifies.
+    for k, v in errs.items():
+        assert v < 3e-3, (k, v)
+    sd = model.state_dict()
+    for k, v in newbuf.items():
+        assert rel_err(sd[k].float(), v.float()) < 2e-3, k
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(B=2, H=136, W=168, nc=71, dilation=(False, False, False), audio="vgg", in_plane=1, frames=96),
+    dict(B=3, H=72, W=104, nc=22, dilation=(False, True, True), audio="vgg", in_plane=1, frames=96),
+    dict(B=1, H=96, W=128, nc=2, dilation=(False, False, False), audio="vgg", in_plane=1, frames=96),
+])
+def test_eval_batch_and_odd_size_match_oracle(cfg):
+    from oracle import cavp_oracle as O
+    model = build_model(cfg).eval()
+    batch = batch_for(cfg)
+    B = cfg["B"]
+    pred, fusion, pack = model(batch["image"].cuda(), batch["audio"][:B].cuda(), eval_mode=True)
+    sd = schema.seeded_state(cfg["nc"], "vgg", 1, seed=0)
+    with torch.no_grad():
+        rp, rf, rpack, _ = O.cavp_forward(sd, batch["image"], batch["audio"][:B], dilation_flags=cfg["dilation"],
+                                          train=False)
+    assert pred.shape == rp.shape and fusion.shape == rf.shape
+    assert rel_err(pred, rp) < 1e-4 and rel_err(fusion, rf) < 1e-4 and rel_err(pack["attn_v"], rpack["attn_v"]) < 1e-4
+    top2 = rp.topk(2, dim=1).values
+    safe = (top2[:, 0] - top2[:, 1]) > 1e-4 * float(rp.abs().max())
+    assert torch.equal(pred.argmax(1).cpu()[safe], rp.argmax(1)[safe])
+
+
+def test_forward_audio_path_with_sound_bank_overwrite():
+    """trainer_cavp_vpo_stereo.py:211 usage: B audio rows + shuffle_info, ow_flag=True touches only the SoundBank."""
+    cfg = load_golden("tiny_train_r18_stereo")["config"]
+    model = build_model(cfg).train()
+    batch = batch_for(cfg)
+    B = cfg["B"]
+    info = {"shuffle_idx": batch["shuffle_idx"].cuda(), "mod_idx_map": {0: 3}, "image_label": batch["img_label"].clone().cuda()}
+    out_cat, ctr_cat, pack = model(batch["image"].cuda(), batch["audio"][:B].cuda(), info, True, audio_func=True)
+    assert out_cat.shape == (2 * B, cfg["nc"], cfg["H"], cfg["W"]) and pack["audio"].shape == (2 * B, 304, 1, 1)
+    assert torch.equal(pack["audio"][B:], pack["audio"][:B][batch["shuffle_idx"].cuda()])
+    assert float(model.memory.bank_vault.abs().sum()) > 0  # update_bank queued single-label features
+    out_cat.sum().backward()
+    assert model.audio_backbone.backbone.fc.weight.grad is not None
