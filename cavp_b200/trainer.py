@@ -47,23 +47,20 @@ def train_step(model, image, audio, pix_label, shuffle_pix_label, *, temperature
     nc = m.num_classes
     g = Graph(dev, prec=m.prec, train=True, sync_bn_group=m._sync_group())
     g.profile = profile
-    # ContrastLoss anchor selection first: it depends on the labels only (host-side index logic + torch.randperm as
-    # in the reference), so its index tensors are on their way to the device before the forward kernels are enqueued
-    # and the step has no host<->device synchronisation point.
-    fh, fw = H // 4, W // 4  # stride-4 feature map (layer1 / decoder resolution)
-    if sel is None:
-        sel = contrast_select(pix_label, shuffle_pix_label, (fh, fw), max_views, ignore_index)
-    gpix = labels_sel = None
-    if sel is not None:
-        half, pix, labels = sel
-        gpix = (pix + half * (B * fh * fw)).pin_memory().to(dev, non_blocking=True)
-        labels_sel = labels.pin_memory().to(dev, non_blocking=True)
     if labels_dev is None:
         labels_dev = pix_label.to(dev, torch.int64, non_blocking=True)
     labels_dev = labels_dev.contiguous()
-
     logits, fusion, proj, fea_a, attn = m.build_graph(g, image, audio, shuffle_idx=shuffle_idx, audio_func=audio_func)
-    assert (fusion.h, fusion.w) == (fh, fw), "contrast selection assumed a stride-4 fusion map"
+    # ContrastLoss anchor selection: host-side index logic on the labels (torch.randperm from the global CPU generator,
+    # as in the reference).  It runs while the forward kernels enqueued above execute, and its index tensors go up
+    # through pinned memory with non-blocking copies, so the step has no host<->device synchronisation point.
+    if sel is None:
+        sel = contrast_select(pix_label, shuffle_pix_label, (fusion.h, fusion.w), max_views, ignore_index)
+    gpix = labels_sel = None
+    if sel is not None:
+        half, pix, labels = sel
+        gpix = (pix + half * (B * fusion.h * fusion.w)).pin_memory().to(dev, non_blocking=True)
+        labels_sel = labels.pin_memory().to(dev, non_blocking=True)
     rows = fusion.n
     # forward_cls: full-resolution prediction for all rows (the reference returns it, cavp_model.py:138-141)
     pred = g.upsample_to_nchw(logits, nc, H, W)
