@@ -297,6 +297,19 @@ __global__ void __launch_bounds__(256, 2) gate_bwd_kernel(const float* __restric
   }
 }
 
+// ------------------------------------------------------------------------------------------------ GELU forward
+// y = x * Phi(x) (nn.GELU, exact erf form: timm Mlp act_layer, models/attn.py:138-143, cavp_model.py:123-128).  Runs as its
+// own pass over the fc1 output: 64 erff per thread inside the GEMM epilogue cost more than the whole K = 304 main loop
+// (one warp per scheduler, nothing to hide the dependent FMA chain), here 2048 threads per SM hide it behind HBM.
+__global__ void gelu_fwd_kernel(const float* __restrict__ pre, float* __restrict__ y, long long n4) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 x = reinterpret_cast<const float4*>(pre)[i];
+    auto f = [](float xv) { return 0.5f * xv * (1.f + erff(xv * 0.70710678118654752440f)); };
+    reinterpret_cast<float4*>(y)[i] = make_float4(f(x.x), f(x.y), f(x.z), f(x.w));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ GELU backward
 __global__ void gelu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ pre, float* __restrict__ dx,
                                 long long n4) {
@@ -360,6 +373,12 @@ extern "C" int cavp_gate_bwd(const float* dx, const float* q, const float* k, co
   const float scale = 1.0f / sqrtf(static_cast<float>(C / heads));
   gate_bwd_kernel<<<grid, 256, 2 * rep * 2 * C4 * sizeof(float4), ST(stream)>>>(dx, q, k, v, attn, dq, dk, dv, Bq, rep,
                                                                                  N, C4, D4, scale);
+  CAVP_LAUNCH_CHECK();
+}
+extern "C" int cavp_gelu_fwd(const float* pre, float* y, long long n, void* stream) {
+  if (!pre || !y) return CAVP_ERR_NULL;
+  if ((n & 3) || (reinterpret_cast<uintptr_t>(pre) & 15) || (reinterpret_cast<uintptr_t>(y) & 15)) return CAVP_ERR_ALIGN;
+  gelu_fwd_kernel<<<grid_for(n / 4, 256), 256, 0, ST(stream)>>>(pre, y, n / 4);
   CAVP_LAUNCH_CHECK();
 }
 extern "C" int cavp_gelu_bwd(const float* dy, const float* pre, float* dx, long long n, void* stream) {

@@ -100,11 +100,14 @@ static int dispatch(IgemmParams& p, int prec, long long b_lo_off, cudaStream_t s
       if (rc) return rc;
       rc = make_weight_tmap(&tm_lo, p.w + b_lo_off, p.Ncols, p.K, p.ldw, bn);
       if (rc) return rc;
-      // schedule selection: the persistent warp-specialised kernel wins at PREC=1 (+20 %) but not at
-      // PREC=2, where the tile kernel is bound by shared-memory bandwidth rather than by fill/drain.  CAVP_IGEMM_WS=1/0
-      // forces it on/off.
+      // schedule selection: the persistent warp-specialised kernel wins at PREC=1 (+20 %); at PREC=2
+      // it depends on the shape (below).  CAVP_IGEMM_WS=1/0 forces it on/off.
       static const char* ws_env = getenv("CAVP_IGEMM_WS");
-      const bool use_ws = ws_env ? (ws_env[0] != '0') : (prec == 1);
+      // measured per shape at PREC=2 (profiles/r01_shape_sweep*.log): the persistent schedule wins when a tile has few
+      // k-blocks (its epilogue overlaps the next tile's main loop: K=304 +29 %, K=576 +13 %, K=1216 +8 %) unless the
+      // epilogue fetches a residual; from K ~ 2000 on the tile kernel's producer-side promotion is 4-7 % faster.
+      const int kb_per_item = p.num_kb / (p.splits > 0 ? p.splits : 1);
+      const bool use_ws = ws_env ? (ws_env[0] != '0') : (prec == 1 || (kb_per_item <= 40 && p.res == nullptr && p.act != ACT_GELU && p.act != ACT_SIGMOID));
       if (use_ws) {
         if (prec == 2)
           return bn == 128 ? launch_igemm_ws<128, 2>(p, tm_hi, tm_lo, st) : launch_igemm_ws<64, 2>(p, tm_hi, tm_lo, st);

@@ -96,46 +96,71 @@ __device__ __forceinline__ void store_split(uint32_t hi_addr, uint32_t lo_addr, 
   if (PREC == 2) st_shared_v4(lo_addr, tf32_rn(v.x - h0), tf32_rn(v.y - h1), tf32_rn(v.z - h2), tf32_rn(v.w - h3));
 }
 
-// Column sums of a 32(lanes) x 32(registers) block: after the call lane j holds sum_i v_i[j] in v[0].
-__device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane) {
-#pragma unroll
-  for (int s = 16; s >= 1; s >>= 1) {
-    const bool up = (lane & s) != 0;
-#pragma unroll
-    for (int i = 0; i < s; ++i) {
-      const float send = up ? v[i] : v[i + s];
-      const float keep = up ? v[i + s] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-    }
-  }
-  return v[0];
-}
+// ---- epilogue building blocks.  A warp owns a 32 (rows = lanes) x 32 (columns = registers) chunk of the tile and moves
+// it through a warp-private shared-memory scratch (row stride 36 floats: 16-byte aligned, conflict-free for
+// quarter-warp accesses) so that every global access is four full 128-byte row segments instead of 32 scattered pieces.
+constexpr int EPI_LDS = 36;
 
-// Epilogue from the fp32 register accumulators of one thread (row = m0 + q*32 + lane, HALF columns starting at
-// n0 + group*HALF): scale/shift/residual/activation, optional pre-activation copy, BN sum / sum-of-squares partials,
-// or raw accumulation (split-K).
-// 32 rows (lanes) x 32 columns (registers) -> global rows, transposed through a warp-private shared-memory scratch so
-// that every store instruction writes four full 128-byte row segments instead of 32 scattered 16-byte pieces.
-__device__ __forceinline__ void store_chunk_coalesced(uint32_t scratch, float* ybase, int ldy, int row0, int M,
-                                                      const float (&v)[32], int lane) {
-  constexpr int LDS_ = 36;  // floats per scratch row (16-byte aligned, conflict-free for quarter-warp accesses)
+__device__ __forceinline__ float4 lds_v4(uint32_t addr) {
+  float4 t;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "r"(addr));
+  return t;
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float t;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(addr));
+  return t;
+}
+// registers -> scratch[lane][0..31]
+__device__ __forceinline__ void stage_chunk(uint32_t scratch, const float (&v)[32], int lane) {
   __syncwarp();
 #pragma unroll
   for (int j = 0; j < 32; j += 4)
-    st_shared_v4(scratch + static_cast<uint32_t>((lane * LDS_ + j) * 4), v[j], v[j + 1], v[j + 2], v[j + 3]);
+    st_shared_v4(scratch + static_cast<uint32_t>((lane * EPI_LDS + j) * 4), v[j], v[j + 1], v[j + 2], v[j + 3]);
+  __syncwarp();
+}
+// scratch -> global rows row0 .. row0+31 (those < M), 32 columns starting at ybase
+__device__ __forceinline__ void store_staged(uint32_t scratch, float* ybase, int ldy, int row0, int M, int lane) {
+  const int c4 = lane & 7, rsub = lane >> 3;
+#pragma unroll
+  for (int rr = 0; rr < 8; ++rr) {
+    const int r = rr * 4 + rsub;
+    const float4 t = lds_v4(scratch + static_cast<uint32_t>((r * EPI_LDS + c4 * 4) * 4));
+    if (row0 + r < M) *reinterpret_cast<float4*>(ybase + static_cast<size_t>(r) * ldy + c4 * 4) = t;
+  }
+}
+// v[j] += res[res_row(row0 + lane)][col0 + j] for a full 32 x 32 chunk: coalesced loads, transposed through the scratch
+__device__ __forceinline__ void add_chunk_coalesced(uint32_t scratch, const IgemmParams& p, int row0, int col0,
+                                                    float (&v)[32], int lane) {
   __syncwarp();
   const int c4 = lane & 7, rsub = lane >> 3;
 #pragma unroll
   for (int rr = 0; rr < 8; ++rr) {
     const int r = rr * 4 + rsub;
-    float4 t;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                 : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
-                 : "r"(scratch + static_cast<uint32_t>((r * LDS_ + c4 * 4) * 4)));
-    if (row0 + r < M) *reinterpret_cast<float4*>(ybase + static_cast<size_t>(r) * ldy + c4 * 4) = t;
+    const int rowg = row0 + r;
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (rowg < p.M) {
+      int q_ = p.res_div > 1 ? rowg / p.res_div : rowg;
+      if (p.res_mod > 0) q_ %= p.res_mod;
+      t = *reinterpret_cast<const float4*>(p.res + static_cast<size_t>(q_) * p.ldr + col0 + c4 * 4);
+    }
+    st_shared_v4(scratch + static_cast<uint32_t>((r * EPI_LDS + c4 * 4) * 4), t.x, t.y, t.z, t.w);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const float4 t = lds_v4(scratch + static_cast<uint32_t>((lane * EPI_LDS + j) * 4));
+    v[j] += t.x;
+    v[j + 1] += t.y;
+    v[j + 2] += t.z;
+    v[j + 3] += t.w;
   }
 }
 
+// Epilogue from the fp32 register accumulators of one thread (row = m0 + q*32 + lane, HALF columns starting at
+// n0 + group*HALF): scale/shift/residual/activation, optional pre-activation copy, BN sum / sum-of-squares partials,
+// or raw accumulation (split-K).  Every option is tested ONCE per chunk (uniform branches around straight-line loops):
+// the plain case costs ~60 instructions per 32 x 32 chunk.
 template <int HALF>
 __device__ __forceinline__ void igemm_epilogue(const IgemmParams& p, float (&acc)[HALF], int m0, int n0, int m_tile,
                                                int group, int q, int lane, uint32_t scratch) {
@@ -143,82 +168,106 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmParams& p, float (&acc
   const int row0 = m0 + q * 32;
   const bool row_ok = row < p.M;
   const bool vec_ok = ((p.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
-  size_t res_row = 0;
-  if (p.res) {
-    int rr_ = p.res_div > 1 ? row / p.res_div : row;
-    if (p.res_mod > 0) rr_ %= p.res_mod;
-    res_row = static_cast<size_t>(rr_);
-  }
 #pragma unroll
   for (int cgrp = 0; cgrp < HALF / 32; ++cgrp) {
     const int col0 = n0 + group * HALF + cgrp * 32;
-    if (col0 < p.Ncols) {
-      float v[32];
+    if (col0 >= p.Ncols) continue;
+    const int ncol = p.Ncols - col0 < 32 ? p.Ncols - col0 : 32;  // valid columns of this chunk (warp-uniform)
+    const bool full_chunk = vec_ok && ncol == 32;
+    float v[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = acc[cgrp * 32 + j];
-      float* yrow = p.y + static_cast<size_t>(row) * p.ldy + col0;
-      if (p.splits > 1) {
-        if (row_ok) {
-          if (vec_ok && col0 + 32 <= p.Ncols) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) red_add_v4(yrow + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.Ncols) atomicAdd(yrow + j, v[j]);
-          }
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int col = col0 + j;
-          if (col < p.Ncols) {
-            float t = v[j];
-            if (p.scale) t *= __ldg(p.scale + col);
-            if (p.shift) t += __ldg(p.shift + col);
-            if (p.res && row_ok) t += __ldg(p.res + res_row * p.ldr + col);
-            v[j] = t;
-          } else {
-            v[j] = 0.f;
-          }
-        }
-        const bool full_chunk = vec_ok && col0 + 32 <= p.Ncols;
-        if (p.y_pre) {
-          if (full_chunk && (reinterpret_cast<uintptr_t>(p.y_pre) & 15) == 0) {
-            store_chunk_coalesced(scratch, p.y_pre + static_cast<size_t>(row0) * p.ldy + col0, p.ldy, row0, p.M, v, lane);
-          } else if (row_ok) {
-            float* prow = p.y_pre + static_cast<size_t>(row) * p.ldy + col0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.Ncols) prow[j] = v[j];
-          }
-        }
-        if (p.act != ACT_NONE) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act, p.slope);
-        }
+    for (int j = 0; j < 32; ++j) v[j] = acc[cgrp * 32 + j];
+    float* yrow = p.y + static_cast<size_t>(row) * p.ldy + col0;
+    if (p.splits > 1) {
+      if (row_ok) {
         if (full_chunk) {
-          store_chunk_coalesced(scratch, p.y + static_cast<size_t>(row0) * p.ldy + col0, p.ldy, row0, p.M, v, lane);
-        } else if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) red_add_v4(yrow + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.Ncols) yrow[j] = v[j];
+            if (j < ncol) atomicAdd(yrow + j, v[j]);
         }
-        if (p.stats) {
-          float sq[32];
+      }
+      continue;
+    }
+    if (ncol < 32) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (!row_ok) v[j] = 0.f;
-            sq[j] = v[j] * v[j];
-          }
-          const float s1 = warp_transpose_reduce(v, lane);
-          const float s2 = warp_transpose_reduce(sq, lane);
-          if (col0 + lane < p.Ncols) {
-            float* st = p.stats + static_cast<size_t>(m_tile * 4 + q) * 2 * p.ldstat;
-            st[col0 + lane] = s1;
-            st[p.ldstat + col0 + lane] = s2;
-          }
-        }
+      for (int j = 0; j < 32; ++j)
+        if (j >= ncol) v[j] = 0.f;
+    }
+    // f(j) for the valid columns; the common full chunk carries no per-column predicate
+    auto cols = [&](auto f) {
+      if (ncol == 32) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f(j);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < ncol) f(j);
+      }
+    };
+    if (p.scale) cols([&](int j) { v[j] *= __ldg(p.scale + col0 + j); });
+    if (p.shift) cols([&](int j) { v[j] += __ldg(p.shift + col0 + j); });
+    if (p.res) {
+      if (full_chunk && ((p.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0)) {
+        add_chunk_coalesced(scratch, p, row0, col0, v, lane);
+      } else if (row_ok) {
+        int rr_ = p.res_div > 1 ? row / p.res_div : row;
+        if (p.res_mod > 0) rr_ %= p.res_mod;
+        const float* rrow = p.res + static_cast<size_t>(rr_) * p.ldr + col0;
+        cols([&](int j) { v[j] += __ldg(rrow + j); });
+      }
+    }
+    if (p.y_pre) {
+      if (full_chunk && (reinterpret_cast<uintptr_t>(p.y_pre) & 15) == 0) {
+        stage_chunk(scratch, v, lane);
+        store_staged(scratch, p.y_pre + static_cast<size_t>(row0) * p.ldy + col0, p.ldy, row0, p.M, lane);
+      } else if (row_ok) {
+        float* prow = p.y_pre + static_cast<size_t>(row) * p.ldy + col0;
+        cols([&](int j) { prow[j] = v[j]; });
+      }
+    }
+    switch (p.act) {
+      case ACT_RELU:
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        break;
+      case ACT_LEAKY:
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.slope;
+        break;
+      case ACT_GELU:
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.5f * v[j] * (1.f + erff(v[j] * 0.70710678118654752440f));
+        break;
+      case ACT_SIGMOID:
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + expf(-v[j]));
+        break;
+      default:
+        break;
+    }
+    if (full_chunk || p.stats) stage_chunk(scratch, v, lane);
+    if (full_chunk) {
+      store_staged(scratch, p.y + static_cast<size_t>(row0) * p.ldy + col0, p.ldy, row0, p.M, lane);
+    } else if (row_ok) {
+      cols([&](int j) { yrow[j] = v[j]; });
+    }
+    if (p.stats) {
+      // column sums straight from the staged chunk: lane j adds column j over the valid rows (conflict-free reads)
+      const int nrow = p.M - row0 < 32 ? p.M - row0 : 32;
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll 4
+      for (int r = 0; r < nrow; ++r) {
+        const float t = lds_f32(scratch + static_cast<uint32_t>((r * EPI_LDS + lane) * 4));
+        s1 += t;
+        s2 = fmaf(t, t, s2);
+      }
+      if (lane < ncol) {
+        float* st = p.stats + static_cast<size_t>(m_tile * 4 + q) * 2 * p.ldstat;
+        st[col0 + lane] = s1;
+        st[p.ldstat + col0 + lane] = s2;
       }
     }
   }

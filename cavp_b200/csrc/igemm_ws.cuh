@@ -248,7 +248,7 @@ igemm_ws_kernel(const IgemmParams p, const __grid_constant__ CUtensorMap tm_b_hi
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const uint32_t off = static_cast<uint32_t>((r0 + 16 * i) * 128) + swz;
-          store_split<PREC>(a_hi + off, a_lo + off, cur[i]);
+          store_split_fast<PREC>(a_hi + off, a_lo + off, cur[i]);
         }
         fence_proxy_async();
         mbar_arrive(&full_bar[s]);

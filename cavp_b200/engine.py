@@ -291,10 +291,19 @@ class Graph:
 
     @staticmethod
     def wgrad_splits(P, cout, K):
+        """Split count of the pixel reduction: CTAs = tiles * splits run in waves of one CTA per SM, so the cost is
+        waves * (k-blocks per split + a fixed per-CTA overhead of ~12 k-blocks: setup, pipeline fill, red.add epilogue).
+        A count that lands just past a multiple of 148 CTAs wastes most of a wave (measured: 300 CTAs took 3 waves)."""
         bn = 128 if K > 64 else 64
         tiles = ((cout + 127) // 128) * ((K + bn - 1) // bn)
         num_kb = (P + 31) // 32
-        return max(1, min(num_kb // 4, (2 * NUM_SMS + tiles - 1) // tiles))
+        best, best_cost = 1, None
+        for s in range(1, max(1, min(num_kb // 4, 96)) + 1):
+            waves = (tiles * s + NUM_SMS - 1) // NUM_SMS
+            cost = waves * ((num_kb + s - 1) // s + 12)
+            if best_cost is None or cost < best_cost:
+                best, best_cost = s, cost
+        return best
 
     @staticmethod
     def colreduce_blocks(M, C):
@@ -355,6 +364,15 @@ class Graph:
                           LEAKY_SLOPE)
             if want_stats:
                 self.stats_from_tensor(y, stats)
+        elif act == ACT_GELU and y.ld == co and y.off == 0:
+            # GELU runs as its own HBM-bound pass (csrc/fusion.cu:gelu_fwd_kernel): the GEMM writes the pre-activation
+            # (kept for the backward) with the plain epilogue
+            tgt = pre if pre is not None else y
+            self._igemm(x, wr.operand(), co, K, tgt, geom=geom, shift=bias_t, res=res, res_mod=res_mod,
+                        res_div=res_div, stats_ptr=0, ldstat=0, act=ACT_NONE)
+            self.work(nbytes=8.0 * M * co)
+            self.call("cavp_gelu_fwd", tgt.ptr, y.ptr, M * co)
+            assert stats is None
         else:
             self._igemm(x, wr.operand(), co, K, y, geom=geom, y_pre=pre, shift=bias_t, res=res, res_mod=res_mod,
                         res_div=res_div, stats_ptr=0 if stats is None else stats[1],

@@ -125,6 +125,8 @@ int cavp_gate_fwd(const float* q, const float* k, const float* v, float* x, floa
 /* dk, dv must be pre-zeroed [Bq*rep][C] */
 int cavp_gate_bwd(const float* dx, const float* q, const float* k, const float* v, const float* attn, float* dq,
                   float* dk, float* dv, int Bq, int rep, int N, int C, int heads, void* stream);
+/* y = gelu(pre) (exact erf form), in place allowed; dx = dy * gelu'(pre) */
+int cavp_gelu_fwd(const float* pre, float* y, long long n, void* stream);
 int cavp_gelu_bwd(const float* dy, const float* pre, float* dx, long long n, void* stream);
 
 /* ---- losses (csrc/loss.cu): CrossEntropyLoss(ignore_index) loss/losser.py:60-62; ContrastLoss
@@ -143,6 +145,19 @@ int cavp_infonce_fwd(const float* S, int lds, const long long* labels, int A, fl
                      float* rowneg, float* rowmean, float* loss, void* stream);
 int cavp_infonce_bwd(const float* S, int lds, const long long* labels, int A, float temperature, const float* rowmax,
                      const float* rowneg, const float* gscale, float* G, int ldg, void* stream);
+
+/* ---- fused optimiser steps (csrc/optim.cu) -----------------------------------------------------
+ * Replace torch.optim.SGD(momentum, weight_decay).step() over the 12 visual parameter groups and
+ * torch.optim.Adam.step() over the audio backbone (main_vpo_mono.py:118-125, trainer/trainer_cavp_vpo_mono.py:192-193)
+ * with ONE launch each.  table: device array of 48-byte rows {float* p; const float* g; float* s0; float* s1;
+ * long long n; float lr; float wd} (g == NULL: skipped, like a parameter whose .grad is None); work: device array of
+ * int pairs (table row, chunk index), chunk = cavp_opt_chunk_elems() elements.
+ * SGD: g' = g + wd*p; s0 = momentum*s0 + g'; p -= lr*s0            (dampening 0, no nesterov; s0 starts at zero)
+ * Adam: m = lerp(m, g', 1-beta1); v = beta2*v + (1-beta2)*g'^2; p -= (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps) */
+int cavp_opt_chunk_elems(void);
+int cavp_sgd_multi(const void* table, const int* work, int nwork, float momentum, void* stream);
+int cavp_adam_multi(const void* table, const int* work, int nwork, double beta1, double beta2, double eps,
+                    double bias_correction1, double bias_correction2, void* stream);
 
 #ifdef __cplusplus
 }

@@ -99,3 +99,23 @@ def test_shuffled_labels_match_oracle():
     b = seeded.synthetic_batch(6, 32, 32, 22, seed=5)
     assert torch.equal(shuffled_labels(b["pix_label"], b["img_label"], b["shuffle_idx"]),
                        seeded.shuffled_labels(b["pix_label"], b["img_label"], b["shuffle_idx"]))
+
+
+def test_optimizer_work_list_and_cpu_refusal():
+    """host side of the fused optimisers: the (tensor, chunk) work list covers every element exactly once, and a CPU
+    parameter is refused instead of silently stepping on the host."""
+    from cavp_b200 import _C
+    from cavp_b200.optim import SGD, Adam, build_work
+    chunk = _C.query("cavp_opt_chunk_elems")
+    sizes = [1, chunk - 1, chunk, chunk + 1, 5 * chunk + 7]
+    work = build_work(sizes, chunk)
+    covered = [0] * len(sizes)
+    for t, c in work.tolist():
+        covered[t] += min(chunk, sizes[t] - c * chunk)
+    assert covered == sizes
+    p = torch.nn.Parameter(torch.zeros(8))
+    p.grad = torch.ones(8)
+    for opt in (SGD([p], lr=0.1, momentum=0.9), Adam([p], lr=0.1)):
+        with pytest.raises(RuntimeError):
+            opt.step()
+    assert [g["lr"] for g in SGD([dict(params=[p], lr=0.5)], lr=0.1, momentum=0.9).param_groups] == [0.5]
