@@ -4,6 +4,7 @@
 #include "igemm.cuh"
 #include "igemm_ts.cuh"
 #include "igemm_ws.cuh"
+#include "igemm_ws2.cuh"
 #include "../../include/cavp_b200.h"
 
 namespace cavp {
@@ -86,6 +87,35 @@ static int launch_igemm_ws(const IgemmParams& p, const CUtensorMap& tm_hi, const
   return static_cast<int>(cudaGetLastError());
 }
 
+// CTA-pair kernel: one cluster of 2 per TPC, persistent over (256-row pair tile, n tile, split) work items
+template <int BN, int PREC>
+static int launch_igemm_ws2(const IgemmParams& p, const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, cudaStream_t st) {
+  using Cfg = Ws2Cfg<BN, PREC>;
+  auto kern = igemm_ws2_kernel<BN, PREC>;
+  static int max_pairs = 0;
+  if (max_pairs == 0) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(148, 1, 1);
+    cfg.blockDim = dim3(WS_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    int n = 0;
+    e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);  // cluster size comes from the kernel's __cluster_dims__
+    if (e != cudaSuccess || n < 1) {
+      cudaGetLastError();
+      n = 74;
+    }
+    max_pairs = n;
+  }
+  const int m_tiles = (p.M + BM - 1) / BM;
+  const int m_pairs = (m_tiles + 1) / 2;
+  const int total_work = m_pairs * p.n_tiles * p.splits;
+  const int pairs = total_work < max_pairs ? total_work : max_pairs;
+  kern<<<2 * pairs, WS_THREADS, Cfg::SMEM_BYTES, st>>>(p, tm_hi, tm_lo, total_work, m_pairs);
+  return static_cast<int>(cudaGetLastError());
+}
+
 // b_lo_off > 0: the B operand is pre-split ([hi | lo], lo at w + b_lo_off) and is fetched by TMA
 template <int MODE>
 static int dispatch(IgemmParams& p, int prec, long long b_lo_off, cudaStream_t st) {
@@ -103,11 +133,24 @@ static int dispatch(IgemmParams& p, int prec, long long b_lo_off, cudaStream_t s
       // schedule selection: the persistent warp-specialised kernel wins at PREC=1 (+20 %); at PREC=2
       // it depends on the shape (below).  CAVP_IGEMM_WS=1/0 forces it on/off.
       static const char* ws_env = getenv("CAVP_IGEMM_WS");
-      // measured per shape at PREC=2 (profiles/r01_shape_sweep*.log): the persistent schedule wins when a tile has few
-      // k-blocks (its epilogue overlaps the next tile's main loop: K=304 +29 %, K=576 +13 %, K=1216 +8 %) unless the
-      // epilogue fetches a residual; from K ~ 2000 on the tile kernel's producer-side promotion is 4-7 % faster.
-      const int kb_per_item = p.num_kb / (p.splits > 0 ? p.splits : 1);
-      const bool use_ws = ws_env ? (ws_env[0] != '0') : (prec == 1 || (kb_per_item <= 40 && p.res == nullptr && p.act != ACT_GELU && p.act != ACT_SIGMOID));
+      // Schedule choice, measured per shape at PREC=2 (profiles/r01_shape_sweep_sched.txt):
+      //  * the persistent kernel (ws) beats the one-tile-per-CTA kernel by 5-30 % (its epilogue overlaps the next tile's
+      //    main loop; short-K GEMMs gain most) except when the epilogue fetches a residual or evaluates erf/exp;
+      //  * the CTA-pair kernel (ws2) adds ~5 % on top when there are enough 256-row pair tiles to keep all 74 TPCs busy
+      //    (each SM reads only half of the weight tile from shared memory).
+      // CAVP_IGEMM_WS=0/1/2 forces tile / ws / pair.
+      const int m_tiles_ = (p.M + BM - 1) / BM;
+      const bool heavy_epilogue = (p.res != nullptr && !igemm_inplace_acc(p)) || p.act == ACT_GELU || p.act == ACT_SIGMOID;
+      int sched = prec == 1 ? 1 : (heavy_epilogue ? 0 : ((bn == 128 && m_tiles_ >= 512) ? 2 : 1));
+      if (ws_env) sched = ws_env[0] - '0';
+      if (sched == 2 && bn == 128) {  // CTA-pair kernel: each CTA fetches half of the weight rows
+        rc = make_weight_tmap(&tm_hi, p.w, p.Ncols, p.K, p.ldw, bn / 2);
+        if (rc) return rc;
+        rc = make_weight_tmap(&tm_lo, p.w + b_lo_off, p.Ncols, p.K, p.ldw, bn / 2);
+        if (rc) return rc;
+        return prec == 2 ? launch_igemm_ws2<128, 2>(p, tm_hi, tm_lo, st) : launch_igemm_ws2<128, 1>(p, tm_hi, tm_lo, st);
+      }
+      const bool use_ws = sched >= 1;
       if (use_ws) {
         if (prec == 2)
           return bn == 128 ? launch_igemm_ws<128, 2>(p, tm_hi, tm_lo, st) : launch_igemm_ws<64, 2>(p, tm_hi, tm_lo, st);

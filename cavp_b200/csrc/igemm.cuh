@@ -161,13 +161,21 @@ __device__ __forceinline__ void add_chunk_coalesced(uint32_t scratch, const Igem
 // n0 + group*HALF): scale/shift/residual/activation, optional pre-activation copy, BN sum / sum-of-squares partials,
 // or raw accumulation (split-K).  Every option is tested ONCE per chunk (uniform branches around straight-line loops):
 // the plain case costs ~60 instructions per 32 x 32 chunk.
+// dgrad accumulating into an existing gradient: residual == output, nothing else in the epilogue
+__host__ __device__ __forceinline__ bool igemm_inplace_acc(const IgemmParams& p) {
+  return p.res != nullptr && p.res == p.y && p.ldr == p.ldy && p.res_mod == 0 && p.res_div <= 1 && p.scale == nullptr &&
+         p.shift == nullptr && p.y_pre == nullptr && p.stats == nullptr && p.act == ACT_NONE;
+}
+
 template <int HALF>
 __device__ __forceinline__ void igemm_epilogue(const IgemmParams& p, float (&acc)[HALF], int m0, int n0, int m_tile,
                                                int group, int q, int lane, uint32_t scratch) {
+  if (m0 >= p.M) return;  // a pair kernel's second CTA can own a tile past the last row: nothing to store, no stats rows
   const int row = m0 + q * 32 + lane;
   const int row0 = m0 + q * 32;
   const bool row_ok = row < p.M;
   const bool vec_ok = ((p.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
+  const bool inplace_acc = igemm_inplace_acc(p);
 #pragma unroll
   for (int cgrp = 0; cgrp < HALF / 32; ++cgrp) {
     const int col0 = n0 + group * HALF + cgrp * 32;
@@ -178,16 +186,23 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmParams& p, float (&acc
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = acc[cgrp * 32 + j];
     float* yrow = p.y + static_cast<size_t>(row) * p.ldy + col0;
-    if (p.splits > 1) {
-      if (row_ok) {
-        if (full_chunk) {
+    if (p.splits > 1 || inplace_acc) {
+      // y += v with red.global.add: split-K partial products, and the in-place gradient accumulation of dgrad
+      // (res == y; one writer per element, so still deterministic) without waiting for a residual read
+      if (full_chunk) {
+        stage_chunk(scratch, v, lane);
+        const int c4 = lane & 7, rsub = lane >> 3;
+        float* ybase = p.y + static_cast<size_t>(row0) * p.ldy + col0;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) red_add_v4(yrow + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < ncol) atomicAdd(yrow + j, v[j]);
+        for (int rr = 0; rr < 8; ++rr) {
+          const int r = rr * 4 + rsub;
+          const float4 t = lds_v4(scratch + static_cast<uint32_t>((r * EPI_LDS + c4 * 4) * 4));
+          if (row0 + r < p.M) red_add_v4(ybase + static_cast<size_t>(r) * p.ldy + c4 * 4, t.x, t.y, t.z, t.w);
         }
+      } else if (row_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < ncol) atomicAdd(yrow + j, v[j]);
       }
       continue;
     }
@@ -607,8 +622,8 @@ igemm_kernel(const IgemmParams p, const __grid_constant__ CUtensorMap tm_b_hi, c
 
     igemm_epilogue<HALF>(p, acc, m0, n0, m_tile, group, q, lane, smem_base + static_cast<uint32_t>(warp * 4608));
   } else {
-    // ===================================================== MMA issuer (warp 8, one thread)
-    if (lane == 0) {
+    // ===================================================== MMA issuer (warp 8: converged loop, one elected lane issues)
+    {
       constexpr uint32_t idesc = umma_idesc_tf32(BM, BN, MODE == MODE_WGRAD, MODE == MODE_WGRAD);
       // K-major: 128B swizzle (type 2), LBO field 1, SBO = 1024 (8 rows x 128 B), k-step = +32 B inside the row.
       // MN-major tf32: 128B swizzle with 32B base (type 1), LBO = 4096 (next 32-wide MN atom), SBO = 512 (next 4 k-rows),
@@ -617,6 +632,11 @@ igemm_kernel(const IgemmParams p, const __grid_constant__ CUtensorMap tm_b_hi, c
       constexpr uint32_t LBO = (MODE == MODE_WGRAD) ? 4096u : 16u;
       constexpr uint32_t SBO = (MODE == MODE_WGRAD) ? 512u : 1024u;
       constexpr uint32_t KSTEP = (MODE == MODE_WGRAD) ? 1024u : 32u;
+      // descriptors of stage 0; stage s / k-step kk only add to the 14-bit start-address field (bytes >> 4)
+      const uint64_t d_a_hi0 = umma_desc(smem_base, LBO, SBO, LAYOUT);
+      const uint64_t d_a_lo0 = umma_desc(smem_base + Cfg::A_BYTES, LBO, SBO, LAYOUT);
+      const uint64_t d_b_hi0 = umma_desc(smem_base + Cfg::A_BYTES * PREC, LBO, SBO, LAYOUT);
+      const uint64_t d_b_lo0 = umma_desc(smem_base + Cfg::A_BYTES * PREC + Cfg::B_BYTES, LBO, SBO, LAYOUT);
       for (int it = 0; it < nkb; ++it) {
         const int s = it % Cfg::STAGES;
         const int u = PROMOTE ? (it >> 1) : 0;
@@ -629,28 +649,24 @@ igemm_kernel(const IgemmParams p, const __grid_constant__ CUtensorMap tm_b_hi, c
         }
         mbar_wait(&full_bar[s], (it / Cfg::STAGES) & 1);
         tc_fence_after();
-        const uint32_t tacc = tmem_base + static_cast<uint32_t>(b * BN);
-        const uint32_t stage = smem_base + s * Cfg::STAGE_BYTES;
-        const uint32_t a_hi = stage, a_lo = stage + Cfg::A_BYTES;
-        const uint32_t b_hi = stage + Cfg::A_BYTES * PREC, b_lo = b_hi + Cfg::B_BYTES;
+        if (elect_one_sync()) {
+          const uint32_t tacc = tmem_base + static_cast<uint32_t>(b * BN);
+          const uint64_t soff = static_cast<uint64_t>((s * Cfg::STAGE_BYTES) >> 4);
 #pragma unroll
-        for (int kk = 0; kk < BK / UMMA_K; ++kk) {
-          const uint32_t koff = kk * KSTEP;
-          const uint64_t da_hi = umma_desc(a_hi + koff, LBO, SBO, LAYOUT);
-          const uint64_t db_hi = umma_desc(b_hi + koff, LBO, SBO, LAYOUT);
-          mma_tf32_ss(tacc, da_hi, db_hi, idesc, !(unit_first && kk == 0));
-          if (PREC == 2) {
-            const uint64_t da_lo = umma_desc(a_lo + koff, LBO, SBO, LAYOUT);
-            const uint64_t db_lo = umma_desc(b_lo + koff, LBO, SBO, LAYOUT);
-            mma_tf32_ss(tacc, da_lo, db_hi, idesc, 1);
-            mma_tf32_ss(tacc, da_hi, db_lo, idesc, 1);
+          for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+            const uint64_t off = soff + ((kk * KSTEP) >> 4);
+            mma_tf32_ss(tacc, d_a_hi0 + off, d_b_hi0 + off, idesc, !(unit_first && kk == 0));
+            if (PREC == 2) {
+              mma_tf32_ss(tacc, d_a_lo0 + off, d_b_hi0 + off, idesc, 1);
+              mma_tf32_ss(tacc, d_a_hi0 + off, d_b_lo0 + off, idesc, 1);
+            }
           }
+          tc_commit(&empty_bar[s]);
+          if (unit_last) tc_commit(&accf_bar[b]);
         }
-        tc_commit(&empty_bar[s]);
-        if (unit_last) tc_commit(&accf_bar[b]);
+        __syncwarp();
       }
     }
-    __syncwarp();
   }
 
   tc_fence_before();

@@ -1,59 +1,54 @@
-// Persistent, fully warp-specialised forward / dgrad implicit-GEMM kernel (weights by TMA, activations gathered).
+// CTA-pair version of the persistent warp-specialised forward / dgrad implicit-GEMM kernel (igemm_ws.cuh).
 //
-// Same math, operand layouts and epilogue as igemm_kernel<BN, PREC, MODE_ROW, BTMA=true> (igemm.cuh); what changes is
-// the schedule.  In igemm_kernel the producer warps also own the fp32 accumulators, so the pipeline fills and drains
-// once per tile and nothing overlaps the epilogue - expensive for the many short-K GEMMs of the fusion block (K = 304:
-// 10 k-blocks per tile).  Here one CTA per SM loops over tiles and the roles never stop:
+// Why: at PREC=2 a 128 x 128 tile moves 160 KB through shared memory per k-block (64 KB of hi/lo operand writes + 96 KB
+// of tcgen05.mma operand reads) against 768 clk of MMA time - the kernel sits on the 128 B/clk shared-memory port, not
+// on the tensor pipe (measured 49 % tensor-pipe active).  A pair of CTAs on the two SMs of a TPC issuing ONE
+// tcgen05.mma.cta_group::2 (M = 256: 128 rows per CTA, N = 128: 64 weight rows per CTA) halves the B-operand traffic
+// per SM: 32 KB A writes + 16 KB B writes + 72 KB operand reads = 120 KB per k-block and SM.
 //
-//   warps  0-3  (WG0, 232 regs): promotion + epilogue.  Thread = tile row; pulls every finished 64-wide K unit out of the
-//                                4-deep TMEM ring (tcgen05.ld), adds it round-to-nearest into BN fp32 registers, runs the
-//                                epilogue of tile t while the MMAs of tile t+1 already fill the ring.
-//   warps  4-11 (WG1-2, 112 regs): producers, two groups alternating k-blocks: cached-offset gather -> register double
-//                                buffer -> TF32 hi/lo split -> swizzled smem; one thread per group issues the weight TMA.
-//   warp   12   (WG3, 40 regs):  MMA issuer.  warps 13-15 idle (they only exist so that setmaxnreg can rebalance registers
-//                                between warpgroups).
-// The smem stage ring, the TMEM ring and all mbarrier phases run continuously across tiles (global k-block / unit counters).
+// Roles per CTA (same thread layout as igemm_ws): warps 0-3 promotion + epilogue of the CTA's own 128 rows, warps 4-11
+// activation producers (two groups alternating k-blocks), warp 12 = MMA issuer (leader CTA only; idle in the peer).
+// Cross-CTA protocol (all barriers at the same shared-memory offsets in both CTAs):
+//   full[s]   leader only.  9 arrivals per phase: lane 0 of each of the 4 warps of the producing group of EACH CTA (after
+//             fence.proxy.async + __syncwarp) + the leader's arrive.expect_tx covering both weight halves; the peer's
+//             TMA completes its bytes on the leader's barrier (cp.async.bulk.tensor...cta_group::2).
+//   empty[s]  both CTAs, armed by ONE multicast tcgen05.commit of the leader.
+//   accf[b]   both CTAs, multicast commit: the 64-wide K unit in TMEM buffer b is complete (each CTA holds its rows).
+//   acce[b]   leader only.  8 arrivals: one per promotion warp of both CTAs once the unit has been read out of TMEM.
 #pragma once
-#include "igemm.cuh"
+#include "igemm_ws.cuh"
 
 namespace cavp {
 
-constexpr int WS_THREADS = 512;
-constexpr int WS_EPI_WARPS = 4;
-constexpr int WS_PROD_WARP0 = 4;
-constexpr int WS_MMA_WARP = 12;
-
 template <int BN, int PREC>
-struct WsCfg {
+struct Ws2Cfg {
   static constexpr bool PROMOTE = (PREC == 2);
   static constexpr int NBUF = 512 / BN >= 4 ? 4 : 512 / BN;
+  static constexpr int BH = BN / 2;  // weight rows held by one CTA
   static constexpr int A_BYTES = BM * 128;
-  static constexpr int B_BYTES = BN * 128;
+  static constexpr int B_BYTES = BH * 128;
   static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * PREC;
-  static constexpr int STAGES = (PREC == 2) ? (BN >= 128 ? 3 : 4) : 4;
+  static constexpr int STAGES = (PREC == 2) ? 4 : 6;
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
   static constexpr int BAR_BYTES = 256;
   static constexpr int ROWTAB_BYTES = BM * 8;
   static constexpr int SCRATCH_BYTES = WS_EPI_WARPS * 4608;
   static constexpr int SMEM_BYTES = RING_BYTES + BAR_BYTES + ROWTAB_BYTES + SCRATCH_BYTES + 1024;
   static constexpr int TMEM_COLS = 512;
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+  static_assert(2 * STAGES + 2 * NBUF + 1 <= BAR_BYTES / 8, "barrier area");
 };
 
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-struct WsWork {
-  int m_tile, n_tile, kb_begin, nkb;
+struct Ws2Work {
+  int m_pair, n_tile, kb_begin, nkb;
 };
-__device__ __forceinline__ WsWork ws_decode(const IgemmParams& p, int w) {
-  // work item = (tile, split); tiles ordered n-fastest so that concurrently running CTAs share their A rows in L2
-  WsWork r;
-  const int tiles = p.n_tiles * ((p.M + BM - 1) / BM);
+__device__ __forceinline__ Ws2Work ws2_decode(const IgemmParams& p, int w, int m_pairs) {
+  Ws2Work r;
+  const int tiles = p.n_tiles * m_pairs;
   const int split = w / tiles;
   const int tile = w - split * tiles;
   r.n_tile = tile % p.n_tiles;
-  r.m_tile = tile / p.n_tiles;
+  r.m_pair = tile / p.n_tiles;
   r.kb_begin = static_cast<int>((static_cast<long long>(p.num_kb) * split) / p.splits);
   const int kb_end = static_cast<int>((static_cast<long long>(p.num_kb) * (split + 1)) / p.splits);
   r.nkb = kb_end - r.kb_begin;
@@ -61,13 +56,13 @@ __device__ __forceinline__ WsWork ws_decode(const IgemmParams& p, int w) {
 }
 
 template <int BN, int PREC>
-__global__ void __launch_bounds__(WS_THREADS, 1)
-igemm_ws_kernel(const IgemmParams p, const __grid_constant__ CUtensorMap tm_b_hi,
-                const __grid_constant__ CUtensorMap tm_b_lo, int total_work) {
-  using Cfg = WsCfg<BN, PREC>;
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WS_THREADS, 1)
+igemm_ws2_kernel(const IgemmParams p, const __grid_constant__ CUtensorMap tm_b_hi,
+                 const __grid_constant__ CUtensorMap tm_b_lo, int total_work, int m_pairs) {
+  using Cfg = Ws2Cfg<BN, PREC>;
   constexpr bool PROMOTE = Cfg::PROMOTE;
   constexpr int NBUF = Cfg::NBUF;
-  static_assert(BN == 64 || BN == 128, "BN must be 64 or 128");
+  static_assert(BN == 128, "pair kernel: 128-column tiles (64 weight rows per CTA)");
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -84,15 +79,18 @@ igemm_ws_kernel(const IgemmParams p, const __grid_constant__ CUtensorMap tm_b_hi
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();  // 0 = leader (issues the MMAs)
+  const int pair_id = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
 
   if (tid == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
-      mbar_init(&full_bar[s], GROUP_THREADS + 1);
+      mbar_init(&full_bar[s], 2 * (GROUP_THREADS / 32) + 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int b = 0; b < NBUF; ++b) {
       mbar_init(&accf_bar[b], 1);
-      mbar_init(&acce_bar[b], WS_EPI_WARPS * 32);
+      mbar_init(&acce_bar[b], 2 * WS_EPI_WARPS);
     }
     fence_mbar_init();
   }
@@ -100,9 +98,10 @@ igemm_ws_kernel(const IgemmParams p, const __grid_constant__ CUtensorMap tm_b_hi
     tma_prefetch_desc(&tm_b_hi);
     if (PREC == 2) tma_prefetch_desc(&tm_b_lo);
   }
-  if (warp == WS_MMA_WARP) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  if (warp == WS_MMA_WARP) tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -113,8 +112,9 @@ igemm_ws_kernel(const IgemmParams p, const __grid_constant__ CUtensorMap tm_b_hi
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
     const uint32_t scratch = scratch_base + static_cast<uint32_t>(warp * 4608);
     int ubase = 0;
-    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-      const WsWork wk = ws_decode(p, w);
+    for (int w = pair_id; w < total_work; w += num_pairs) {
+      const Ws2Work wk = ws2_decode(p, w, m_pairs);
+      const int m_tile = wk.m_pair * 2 + static_cast<int>(rank);
       const int nunits = PROMOTE ? ((wk.nkb + 1) >> 1) : 1;
       float acc[BN];
 #pragma unroll
@@ -132,10 +132,11 @@ igemm_ws_kernel(const IgemmParams p, const __grid_constant__ CUtensorMap tm_b_hi
           for (int j = 0; j < 32; ++j) acc[cg * 32 + j] += v[j];
         }
         tc_fence_before();
-        mbar_arrive(&acce_bar[b]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&acce_bar[b]), 0));
       }
       ubase += nunits;
-      igemm_epilogue<BN>(p, acc, wk.m_tile * BM, wk.n_tile * BN, wk.m_tile, 0, q, lane, scratch);
+      igemm_epilogue<BN>(p, acc, m_tile * BM, wk.n_tile * BN, m_tile, 0, q, lane, scratch);
     }
   } else if (warp < WS_MMA_WARP) {
     // ================================================================= producers
@@ -147,10 +148,10 @@ igemm_ws_kernel(const IgemmParams p, const __grid_constant__ CUtensorMap tm_b_hi
     const int r0 = gtid >> 3;
     const uint32_t swz = static_cast<uint32_t>((c ^ (r0 & 7)) << 4);
     int gbase = 0;  // global k-block counter at the start of the current work item
-    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-      const WsWork wk = ws_decode(p, w);
-      const int m0 = wk.m_tile * BM, n0 = wk.n_tile * BN;
-      // ---- row table of this tile (all producers have finished reading the previous one)
+    for (int w = pair_id; w < total_work; w += num_pairs) {
+      const Ws2Work wk = ws2_decode(p, w, m_pairs);
+      const int m0 = (wk.m_pair * 2 + static_cast<int>(rank)) * BM;
+      const int nb0 = wk.n_tile * BN + static_cast<int>(rank) * Cfg::BH;  // first weight row of this CTA's half
       named_bar_sync(1, PRODUCER_THREADS);
       if (ptid < BM) {
         const int m = m0 + ptid;
@@ -239,11 +240,13 @@ igemm_ws_kernel(const IgemmParams p, const __grid_constant__ CUtensorMap tm_b_hi
         const int s = G % Cfg::STAGES;
         mbar_wait(&empty_bar[s], (((G / Cfg::STAGES) & 1) ^ 1));
         const uint32_t a_hi = smem_base + s * Cfg::STAGE_BYTES, a_lo = a_hi + Cfg::A_BYTES;
+        const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[s]), 0);
         if (gtid == 0) {
           const uint32_t b_hi = a_hi + Cfg::A_BYTES * PREC;
-          mbar_arrive_expect_tx(&full_bar[s], Cfg::B_BYTES * PREC);
-          tma_load_2d(b_hi, &tm_b_hi, &full_bar[s], (wk.kb_begin + it) * BK, n0);
-          if (PREC == 2) tma_load_2d(b_hi + Cfg::B_BYTES, &tm_b_lo, &full_bar[s], (wk.kb_begin + it) * BK, n0);
+          // the leader accounts for the weight bytes of both halves; each CTA fetches its own 64 rows
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * Cfg::B_BYTES * PREC);
+          tma_load_2d_pair(b_hi, &tm_b_hi, full_leader, (wk.kb_begin + it) * BK, nb0);
+          if (PREC == 2) tma_load_2d_pair(b_hi + Cfg::B_BYTES, &tm_b_lo, full_leader, (wk.kb_begin + it) * BK, nb0);
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -251,7 +254,8 @@ igemm_ws_kernel(const IgemmParams p, const __grid_constant__ CUtensorMap tm_b_hi
           store_split_fast<PREC>(a_hi + off, a_lo + off, cur[i]);
         }
         fence_proxy_async();
-        mbar_arrive(&full_bar[s]);
+        __syncwarp();  // every lane of the warp has written and fenced its rows
+        if (lane == 0) mbar_arrive_cluster(full_leader);
       };
       if (group < wk.nkb) {
         a_seek(group);
@@ -264,17 +268,17 @@ igemm_ws_kernel(const IgemmParams p, const __grid_constant__ CUtensorMap tm_b_hi
       gbase += wk.nkb;
     }
   } else {
-    // ================================================================= MMA issuer (warp 12, one thread) + idle warps
+    // ================================================================= MMA issuer (leader CTA, warp 12, one thread)
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    if (warp == WS_MMA_WARP) {  // converged loop; one elected lane issues the tcgen05 instructions
-      constexpr uint32_t idesc = umma_idesc_tf32(BM, BN, 0, 0);
+    if (rank == 0 && warp == WS_MMA_WARP) {  // converged loop; one elected lane issues the tcgen05 instructions
+      constexpr uint32_t idesc = umma_idesc_tf32(2 * BM, BN, 0, 0);
       const uint64_t d_a_hi0 = umma_desc(smem_base, 16, 1024, 2);
       const uint64_t d_a_lo0 = umma_desc(smem_base + Cfg::A_BYTES, 16, 1024, 2);
       const uint64_t d_b_hi0 = umma_desc(smem_base + Cfg::A_BYTES * PREC, 16, 1024, 2);
       const uint64_t d_b_lo0 = umma_desc(smem_base + Cfg::A_BYTES * PREC + Cfg::B_BYTES, 16, 1024, 2);
       int gbase = 0, ubase = 0;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-        const WsWork wk = ws_decode(p, w);
+      for (int w = pair_id; w < total_work; w += num_pairs) {
+        const Ws2Work wk = ws2_decode(p, w, m_pairs);
         for (int it = 0; it < wk.nkb; ++it) {
           const int G = gbase + it;
           const int s = G % Cfg::STAGES;
@@ -283,10 +287,10 @@ igemm_ws_kernel(const IgemmParams p, const __grid_constant__ CUtensorMap tm_b_hi
           const bool unit_first = PROMOTE ? ((it & 1) == 0) : (it == 0);
           const bool unit_last = PROMOTE ? ((it & 1) == 1 || it == wk.nkb - 1) : (it == wk.nkb - 1);
           if (unit_first) {
-            mbar_wait(&acce_bar[b], (((U / NBUF) & 1) ^ 1));
+            mbar_wait_cluster(&acce_bar[b], (((U / NBUF) & 1) ^ 1));
             tc_fence_after();
           }
-          mbar_wait(&full_bar[s], (G / Cfg::STAGES) & 1);
+          mbar_wait_cluster(&full_bar[s], (G / Cfg::STAGES) & 1);
           tc_fence_after();
           if (elect_one_sync()) {
             const uint32_t tacc = tmem_base + static_cast<uint32_t>(b * BN);
@@ -294,14 +298,14 @@ igemm_ws_kernel(const IgemmParams p, const __grid_constant__ CUtensorMap tm_b_hi
 #pragma unroll
             for (int kk = 0; kk < BK / UMMA_K; ++kk) {
               const uint64_t off = soff + kk * 2;
-              mma_tf32_ss(tacc, d_a_hi0 + off, d_b_hi0 + off, idesc, !(unit_first && kk == 0));
+              mma_tf32_ss_pair(tacc, d_a_hi0 + off, d_b_hi0 + off, idesc, !(unit_first && kk == 0));
               if (PREC == 2) {
-                mma_tf32_ss(tacc, d_a_lo0 + off, d_b_hi0 + off, idesc, 1);
-                mma_tf32_ss(tacc, d_a_hi0 + off, d_b_lo0 + off, idesc, 1);
+                mma_tf32_ss_pair(tacc, d_a_lo0 + off, d_b_hi0 + off, idesc, 1);
+                mma_tf32_ss_pair(tacc, d_a_hi0 + off, d_b_lo0 + off, idesc, 1);
               }
             }
-            tc_commit(&empty_bar[s]);
-            if (unit_last) tc_commit(&accf_bar[b]);
+            tc_commit_pair(&empty_bar[s], 3);
+            if (unit_last) tc_commit_pair(&accf_bar[b], 3);
           }
           __syncwarp();
         }
@@ -314,7 +318,8 @@ igemm_ws_kernel(const IgemmParams p, const __grid_constant__ CUtensorMap tm_b_hi
 
   tc_fence_before();
   __syncthreads();
-  if (warp == WS_MMA_WARP) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  cluster_sync_all();  // the peer may still be reading TMEM / receiving commits until both CTAs are through
+  if (warp == WS_MMA_WARP) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
 }
 
 }  // namespace cavp

@@ -69,6 +69,9 @@ def time_it(fn, iters):
     return e0.elapsed_time(e1) / iters
 
 
+LDX0 = [False]  # --ldx0: every A row reads the same address (L1 hits): the no-global-latency ceiling of the main loop
+
+
 def run_case(case, prec, iters):
     name, kind, nimg, h, c, ncols, r, stride, pad, dil, fl = case
     K = r * r * c
@@ -92,7 +95,7 @@ def run_case(case, prec, iters):
 
         def fn():
             _C.call("cavp_igemm", _C.ptr(x), _C.ptr(sp[0]), _C.ptr(y), _C.ptr(ypre), 0, _C.ptr(shift), _C.ptr(res),
-                    _C.ptr(st), nimg, h, h, c, c, ho, ho, r, r, stride, pad, dil, dgrad, ncols, K, ncols,
+                    _C.ptr(st), nimg, h, h, c, 0 if LDX0[0] else c, ho, ho, r, r, stride, pad, dil, dgrad, ncols, K, ncols,
                     ncols if res is not None else 0, 0, 0, ncols, act, 0.01, splits, prec, sp[0].numel(), _C.stream())
         flops = 2.0 * M * ncols * K
     else:
@@ -119,7 +122,9 @@ def main():
     ap.add_argument("--only", default=None)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--json", default=None)
+    ap.add_argument("--ldx0", action="store_true")
     args = ap.parse_args()
+    LDX0[0] = args.ldx0
     out = {}
     env = {k: v for k, v in os.environ.items() if k.startswith("CAVP_")}
     print(f"# shape sweep prec={args.prec} env={env}", flush=True)
