@@ -38,6 +38,21 @@ static int make_weight_tmap(CUtensorMap* tm, const float* w, int rows, int K, in
   return r == CUDA_SUCCESS ? 0 : 1000 + static_cast<int>(r);
 }
 
+// dense [P][cout] fp32 matrix (the pre-split dY of a weight gradient), box = 32 channels x 32 pixels, 128-byte swizzle
+// with 32-byte atoms = the shared-memory layout of an MN-major tf32 UMMA operand
+static int make_dy_tmap(CUtensorMap* tm, const float* dy, long long P, int cout) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return CAVP_ERR_ARG;
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cout), static_cast<cuuint64_t>(P)};
+  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(cout) * 4};
+  cuuint32_t box[2] = {32, static_cast<cuuint32_t>(BK)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(dy), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 1000 + static_cast<int>(r);
+}
+
 template <int BN, int PREC, int MODE, bool BTMA>
 static int launch_igemm(const IgemmParams& p, const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, cudaStream_t st) {
   using Cfg = TileCfg<BN, PREC>;
@@ -169,6 +184,19 @@ static int dispatch(IgemmParams& p, int prec, long long b_lo_off, cudaStream_t s
                        : launch_igemm<64, 1, MODE, true>(p, tm_hi, tm_lo, st);
     }
   }
+  if constexpr (MODE == MODE_WGRAD) {
+    if (b_lo_off > 0) {  // dY pre-split and dense: fetched by TMA
+      int rc = make_dy_tmap(&tm_hi, p.w, p.red_len, p.M);
+      if (rc) return rc;
+      rc = make_dy_tmap(&tm_lo, p.w + b_lo_off, p.red_len, p.M);
+      if (rc) return rc;
+      if (prec == 2)
+        return bn == 128 ? launch_igemm<128, 2, MODE, true>(p, tm_hi, tm_lo, st)
+                         : launch_igemm<64, 2, MODE, true>(p, tm_hi, tm_lo, st);
+      return bn == 128 ? launch_igemm<128, 1, MODE, true>(p, tm_hi, tm_lo, st)
+                       : launch_igemm<64, 1, MODE, true>(p, tm_hi, tm_lo, st);
+    }
+  }
   if (prec == 2)
     return bn == 128 ? launch_igemm<128, 2, MODE, false>(p, tm_hi, tm_lo, st)
                      : launch_igemm<64, 2, MODE, false>(p, tm_hi, tm_lo, st);
@@ -182,6 +210,22 @@ __global__ void split_tf32_kernel(const float* __restrict__ w, float* __restrict
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float4 v = reinterpret_cast<const float4*>(w)[i];
+    const float h0 = tf32_rn(v.x), h1 = tf32_rn(v.y), h2 = tf32_rn(v.z), h3 = tf32_rn(v.w);
+    reinterpret_cast<float4*>(hi)[i] = make_float4(h0, h1, h2, h3);
+    reinterpret_cast<float4*>(lo)[i] =
+        make_float4(tf32_rn(v.x - h0), tf32_rn(v.y - h1), tf32_rn(v.z - h2), tf32_rn(v.w - h3));
+  }
+}
+
+// strided source [rows][ld] (a channel window of a gradient buffer) -> dense hi / lo [rows][cols]
+__global__ void split_tf32_2d_kernel(const float* __restrict__ src, int ld, long long rows, int cols4,
+                                     float* __restrict__ hi, float* __restrict__ lo) {
+  const long long n4 = rows * cols4;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / cols4;
+    const int c = static_cast<int>(i - r * cols4);
+    const float4 v = *reinterpret_cast<const float4*>(src + r * ld + c * 4);
     const float h0 = tf32_rn(v.x), h1 = tf32_rn(v.y), h2 = tf32_rn(v.z), h3 = tf32_rn(v.w);
     reinterpret_cast<float4*>(hi)[i] = make_float4(h0, h1, h2, h3);
     reinterpret_cast<float4*>(lo)[i] =
@@ -227,9 +271,41 @@ extern "C" int cavp_igemm(const float* x, const float* w, float* y, float* y_pre
   return dispatch<MODE_ROW>(p, prec, b_lo_off, static_cast<cudaStream_t>(stream));
 }
 
+static int wgrad_impl(const float* dy, const float* x, float* dw, int nimg, int hs, int ws, int c, int ldx, int ho,
+                      int wo, int r, int s, int stride, int pad, int dil, int cout, int lddy, int splits, int prec,
+                      long long dy_lo_off, void* stream);
+
 extern "C" int cavp_igemm_wgrad(const float* dy, const float* x, float* dw, int nimg, int hs, int ws, int c, int ldx,
                                 int ho, int wo, int r, int s, int stride, int pad, int dil, int cout, int lddy,
                                 int splits, int prec, void* stream) {
+  return wgrad_impl(dy, x, dw, nimg, hs, ws, c, ldx, ho, wo, r, s, stride, pad, dil, cout, lddy, splits, prec, 0, stream);
+}
+
+extern "C" int cavp_igemm_wgrad_tma(const float* dy_hi, long long dy_lo_off, const float* x, float* dw, int nimg, int hs,
+                                    int ws, int c, int ldx, int ho, int wo, int r, int s, int stride, int pad, int dil,
+                                    int cout, int splits, int prec, void* stream) {
+  if (dy_lo_off <= 0 || (dy_lo_off & 3)) return CAVP_ERR_ARG;
+  return wgrad_impl(dy_hi, x, dw, nimg, hs, ws, c, ldx, ho, wo, r, s, stride, pad, dil, cout, cout, splits, prec,
+                    dy_lo_off, stream);
+}
+
+extern "C" int cavp_split_tf32_2d(const float* src, int ld, long long rows, int cols, float* hi, float* lo,
+                                  void* stream) {
+  if (!src || !hi || !lo) return CAVP_ERR_NULL;
+  if ((cols & 3) || (ld & 3) || (reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(hi) & 15) ||
+      (reinterpret_cast<uintptr_t>(lo) & 15))
+    return CAVP_ERR_ALIGN;
+  long long blocks = (rows * (cols / 4) + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  split_tf32_2d_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, ld, rows,
+                                                                                                    cols / 4, hi, lo);
+  return static_cast<int>(cudaGetLastError());
+}
+
+static int wgrad_impl(const float* dy, const float* x, float* dw, int nimg, int hs, int ws, int c, int ldx, int ho,
+                      int wo, int r, int s, int stride, int pad, int dil, int cout, int lddy, int splits, int prec,
+                      long long dy_lo_off, void* stream) {
   if (!dy || !x || !dw) return CAVP_ERR_NULL;
   if ((c & 3) || (ldx & 3) || (cout & 3) || (lddy & 3)) return CAVP_ERR_ALIGN;
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(dy) & 15)) return CAVP_ERR_ALIGN;
@@ -245,7 +321,7 @@ extern "C" int cavp_igemm_wgrad(const float* dy, const float* x, float* dw, int 
   p.num_kb = (p.red_len + BK - 1) / BK;
   p.splits = splits < 1 ? 1 : (splits > p.num_kb ? p.num_kb : splits);
   fill_divs(p);
-  return dispatch<MODE_WGRAD>(p, prec, 0, static_cast<cudaStream_t>(stream));
+  return dispatch<MODE_WGRAD>(p, prec, dy_lo_off, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int cavp_split_tf32(const float* w, float* hi, float* lo, long long n, void* stream) {

@@ -292,7 +292,8 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmParams& p, float (&acc
 template <int BN, int PREC, int MODE, bool BTMA>
 __global__ void __launch_bounds__(CTA_THREADS, 1)
 igemm_kernel(const IgemmParams p, const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo) {
-  static_assert(!BTMA || MODE == MODE_ROW, "TMA B operand only for the row-major (weights) mode");
+  // BTMA: MODE_ROW - the weight operand (B) is pre-split in HBM and fetched by TMA; MODE_WGRAD - the dY operand (A,
+  // MN-major) is pre-split and fetched by TMA (four 32-column atoms per k-block), the producers only gather im2col(X)
   using Cfg = TileCfg<BN, PREC>;
   constexpr bool PROMOTE = Cfg::PROMOTE;
   constexpr int NBUF = Cfg::NBUF;
@@ -487,7 +488,7 @@ igemm_kernel(const IgemmParams p, const __grid_constant__ CUtensorMap tm_b_hi, c
                                         : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    auto load_wgrad = [&](int it, float4 (&va)[8], float4 (&vb)[8]) {
+    auto load_wgrad_ab = [&](int it, float4 (&va)[8], float4 (&vb)[8], const bool with_a) {
       // this warp's k-rows are the 8 consecutive pixels rr*8 .. rr*8+7 of the k-block: decode the first one, then walk
       // (ox, oy, image) incrementally instead of 8 divmod pairs
       const int pixb = (kb_begin + it) * BK + rr * 8;
@@ -501,7 +502,8 @@ igemm_kernel(const IgemmParams p, const __grid_constant__ CUtensorMap tm_b_hi, c
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const bool pok = pixb + i < p.red_len;
-        va[i] = (pok && wg_co_ok) ? ldg_nc_v4(dyp + static_cast<size_t>(i) * p.ldw) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (with_a)
+          va[i] = (pok && wg_co_ok) ? ldg_nc_v4(dyp + static_cast<size_t>(i) * p.ldw) : make_float4(0.f, 0.f, 0.f, 0.f);
         const bool ok = pok && wg_j_ok && static_cast<unsigned>(y) < static_cast<unsigned>(p.Hs) &&
                         static_cast<unsigned>(x) < static_cast<unsigned>(p.Ws);
         vb[i] = ok ? ldg_nc_v4(p.x + static_cast<size_t>(base + y * p.Ws + x) * p.ldx + wg_ci)
@@ -517,6 +519,7 @@ igemm_kernel(const IgemmParams p, const __grid_constant__ CUtensorMap tm_b_hi, c
         }
       }
     };
+    auto load_wgrad = [&](int it, float4 (&va)[8], float4 (&vb)[8]) { load_wgrad_ab(it, va, vb, true); };
     auto store_row_a = [&](int s, const float4 (&va)[8]) {
       const uint32_t a_hi = smem_base + s * Cfg::STAGE_BYTES, a_lo = a_hi + Cfg::A_BYTES;
 #pragma unroll
@@ -535,7 +538,7 @@ igemm_kernel(const IgemmParams p, const __grid_constant__ CUtensorMap tm_b_hi, c
     };
     // MN-major tf32 operands use the 128B swizzle with a 32-byte base: atom = 4 k-rows x 128 B, the 32-byte chunk
     // index is XORed with (k-row & 3).
-    auto store_wgrad = [&](int s, const float4 (&va)[8], const float4 (&vb)[8]) {
+    auto store_wgrad_ab = [&](int s, const float4 (&va)[8], const float4 (&vb)[8], const bool with_a) {
       const uint32_t a_hi = smem_base + s * Cfg::STAGE_BYTES, a_lo = a_hi + Cfg::A_BYTES;
       const uint32_t b_hi = a_hi + Cfg::A_BYTES * PREC, b_lo = b_hi + Cfg::B_BYTES;
       const uint32_t atom_off = static_cast<uint32_t>((cc >> 3) * 4096);
@@ -545,13 +548,49 @@ igemm_kernel(const IgemmParams p, const __grid_constant__ CUtensorMap tm_b_hi, c
         const int r = rr * 8 + i;
         const uint32_t off = atom_off + static_cast<uint32_t>(r * 128) +
                              static_cast<uint32_t>((((c16 >> 1) ^ (r & 3)) << 5) | ((c16 & 1) << 4));
-        store_split_fast<PREC>(a_hi + off, a_lo + off, va[i]);
+        if (with_a) store_split_fast<PREC>(a_hi + off, a_lo + off, va[i]);
         if (cc * 4 < BN) store_split_fast<PREC>(b_hi + off, b_lo + off, vb[i]);
       }
     };
+    auto store_wgrad = [&](int s, const float4 (&va)[8], const float4 (&vb)[8]) { store_wgrad_ab(s, va, vb, true); };
 
     const int npairs = (nkb + 1) >> 1;
-    if (BTMA) {
+    if (BTMA && MODE == MODE_WGRAD) {
+      // dY (pre-split, dense [P][Cout]) arrives by TMA as four 32-channel atoms per k-block, already in the MN-major
+      // 128B/32B-atom swizzle the descriptors expect; the producers gather only im2col(X), register double-buffered.
+      float4 vb0[8], vb1[8], vdummy[8];
+      auto body = [&](int u, float4 (&cur)[8], float4 (&nxt)[8]) {
+        const int it = 2 * u + group;
+        if (it + 2 < nkb) load_wgrad_ab(it + 2, vdummy, nxt, false);
+        if (PROMOTE && u >= 2) promote(u - 2);
+        if (it < nkb) {
+          const int s = it % Cfg::STAGES;
+          mbar_wait(&empty_bar[s], (((it / Cfg::STAGES) & 1) ^ 1));
+          if (gtid < 32) {  // warp-uniform branch + elect: the TMA issue is not wrapped in per-instruction ELECT loops
+            if (elect_one_sync()) {
+              const uint32_t a_hi = smem_base + s * Cfg::STAGE_BYTES;
+              mbar_arrive_expect_tx(&full_bar[s], Cfg::A_BYTES * PREC);
+#pragma unroll
+              for (int atom = 0; atom < BM / 32; ++atom) {
+                tma_load_2d(a_hi + atom * 4096, &tm_b_hi, &full_bar[s], m0 + atom * 32, (kb_begin + it) * BK);
+                if (PREC == 2)
+                  tma_load_2d(a_hi + Cfg::A_BYTES + atom * 4096, &tm_b_lo, &full_bar[s], m0 + atom * 32,
+                              (kb_begin + it) * BK);
+              }
+            }
+            __syncwarp();
+          }
+          store_wgrad_ab(s, vdummy, cur, false);
+          fence_proxy_async();
+          mbar_arrive(&full_bar[s]);
+        }
+      };
+      if (group < nkb) load_wgrad_ab(group, vdummy, vb0, false);
+      for (int u = 0; u < npairs; u += 2) {
+        body(u, vb0, vb1);
+        if (u + 1 < npairs) body(u + 1, vb1, vb0);
+      }
+    } else if (BTMA) {
       // B (pre-split weights) arrives by TMA; A is register double-buffered: the global loads of k-block it+2 are
       // in flight while k-block it is promoted / split / stored.
       float4 va0[8], va1[8];
@@ -565,11 +604,14 @@ igemm_kernel(const IgemmParams p, const __grid_constant__ CUtensorMap tm_b_hi, c
         if (it < nkb) {
           const int s = it % Cfg::STAGES;
           mbar_wait(&empty_bar[s], (((it / Cfg::STAGES) & 1) ^ 1));
-          if (gtid == 0) {
-            const uint32_t b_hi = smem_base + s * Cfg::STAGE_BYTES + Cfg::A_BYTES * PREC;
-            mbar_arrive_expect_tx(&full_bar[s], Cfg::B_BYTES * PREC);
-            tma_load_2d(b_hi, &tm_b_hi, &full_bar[s], (kb_begin + it) * BK, n0);
-            if (PREC == 2) tma_load_2d(b_hi + Cfg::B_BYTES, &tm_b_lo, &full_bar[s], (kb_begin + it) * BK, n0);
+          if (gtid < 32) {
+            if (elect_one_sync()) {
+              const uint32_t b_hi = smem_base + s * Cfg::STAGE_BYTES + Cfg::A_BYTES * PREC;
+              mbar_arrive_expect_tx(&full_bar[s], Cfg::B_BYTES * PREC);
+              tma_load_2d(b_hi, &tm_b_hi, &full_bar[s], (kb_begin + it) * BK, n0);
+              if (PREC == 2) tma_load_2d(b_hi + Cfg::B_BYTES, &tm_b_lo, &full_bar[s], (kb_begin + it) * BK, n0);
+            }
+            __syncwarp();
           }
           store_row_a(s, cur);
           fence_proxy_async();

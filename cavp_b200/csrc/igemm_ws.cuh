@@ -239,11 +239,14 @@ igemm_ws_kernel(const IgemmParams p, const __grid_constant__ CUtensorMap tm_b_hi
         const int s = G % Cfg::STAGES;
         mbar_wait(&empty_bar[s], (((G / Cfg::STAGES) & 1) ^ 1));
         const uint32_t a_hi = smem_base + s * Cfg::STAGE_BYTES, a_lo = a_hi + Cfg::A_BYTES;
-        if (gtid == 0) {
-          const uint32_t b_hi = a_hi + Cfg::A_BYTES * PREC;
-          mbar_arrive_expect_tx(&full_bar[s], Cfg::B_BYTES * PREC);
-          tma_load_2d(b_hi, &tm_b_hi, &full_bar[s], (wk.kb_begin + it) * BK, n0);
-          if (PREC == 2) tma_load_2d(b_hi + Cfg::B_BYTES, &tm_b_lo, &full_bar[s], (wk.kb_begin + it) * BK, n0);
+        if (gtid < 32) {
+          if (elect_one_sync()) {
+            const uint32_t b_hi = a_hi + Cfg::A_BYTES * PREC;
+            mbar_arrive_expect_tx(&full_bar[s], Cfg::B_BYTES * PREC);
+            tma_load_2d(b_hi, &tm_b_hi, &full_bar[s], (wk.kb_begin + it) * BK, n0);
+            if (PREC == 2) tma_load_2d(b_hi + Cfg::B_BYTES, &tm_b_lo, &full_bar[s], (wk.kb_begin + it) * BK, n0);
+          }
+          __syncwarp();
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {

@@ -241,12 +241,15 @@ igemm_ws2_kernel(const IgemmParams p, const __grid_constant__ CUtensorMap tm_b_h
         mbar_wait(&empty_bar[s], (((G / Cfg::STAGES) & 1) ^ 1));
         const uint32_t a_hi = smem_base + s * Cfg::STAGE_BYTES, a_lo = a_hi + Cfg::A_BYTES;
         const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[s]), 0);
-        if (gtid == 0) {
-          const uint32_t b_hi = a_hi + Cfg::A_BYTES * PREC;
-          // the leader accounts for the weight bytes of both halves; each CTA fetches its own 64 rows
-          if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * Cfg::B_BYTES * PREC);
-          tma_load_2d_pair(b_hi, &tm_b_hi, full_leader, (wk.kb_begin + it) * BK, nb0);
-          if (PREC == 2) tma_load_2d_pair(b_hi + Cfg::B_BYTES, &tm_b_lo, full_leader, (wk.kb_begin + it) * BK, nb0);
+        if (gtid < 32) {
+          if (elect_one_sync()) {
+            const uint32_t b_hi = a_hi + Cfg::A_BYTES * PREC;
+            // the leader accounts for the weight bytes of both halves; each CTA fetches its own 64 rows
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * Cfg::B_BYTES * PREC);
+            tma_load_2d_pair(b_hi, &tm_b_hi, full_leader, (wk.kb_begin + it) * BK, nb0);
+            if (PREC == 2) tma_load_2d_pair(b_hi + Cfg::B_BYTES, &tm_b_lo, full_leader, (wk.kb_begin + it) * BK, nb0);
+          }
+          __syncwarp();
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {

@@ -306,6 +306,15 @@ class Graph:
         return best
 
     @staticmethod
+    def wgrad_via_tma(P, cout, K):
+        """The split pass over dY costs 12 B per element; it pays when enough column tiles (K / 128) re-read dY."""
+        import os
+        forced = os.environ.get("CAVP_WGRAD_TMA")
+        if forced is not None:
+            return forced != "0"
+        return K >= 1024 and cout >= 32
+
+    @staticmethod
     def colreduce_blocks(M, C):
         return max(1, min((M + 31) // 32, 4 * NUM_SMS // max(1, (C // 4 + 63) // 64)))
 
@@ -416,9 +425,19 @@ class Graph:
                     wsplits = self.wgrad_splits(M, co, K)
                     if wsplits > 1:
                         self.call("cavp_zero", dwk.data_ptr(), dwk.numel() * 4)
-                    self.work(flops=2.0 * M * co * K, tag=f"wgrad P{M} Cout{co} K{K} k{r} s{stride} d{dil} splits{wsplits}")
-                    self.call("cavp_igemm_wgrad", g.ptr, x.ptr, dwk.data_ptr(), x.n, x.h, x.w, x.c, x.ld, ho, wo, r, s,
-                              stride, pad, dil, co, g.ld, wsplits, self.prec)
+                    if self.wgrad_via_tma(M, co, K):
+                        # dY pre-split once (dense hi | lo) and fetched by TMA by every one of the K/128 column tiles
+                        gsp = self.empty(2, M, co)
+                        self.call("cavp_split_tf32_2d", g.ptr, g.ld, M, co, gsp[0].data_ptr(), gsp[1].data_ptr())
+                        self.work(flops=2.0 * M * co * K,
+                                  tag=f"wgrad(tma) P{M} Cout{co} K{K} k{r} s{stride} d{dil} splits{wsplits}")
+                        self.call("cavp_igemm_wgrad_tma", gsp[0].data_ptr(), gsp[0].numel(), x.ptr, dwk.data_ptr(), x.n,
+                                  x.h, x.w, x.c, x.ld, ho, wo, r, s, stride, pad, dil, co, wsplits, self.prec)
+                    else:
+                        self.work(flops=2.0 * M * co * K,
+                                  tag=f"wgrad P{M} Cout{co} K{K} k{r} s{stride} d{dil} splits{wsplits}")
+                        self.call("cavp_igemm_wgrad", g.ptr, x.ptr, dwk.data_ptr(), x.n, x.h, x.w, x.c, x.ld, ho, wo, r,
+                                  s, stride, pad, dil, co, g.ld, wsplits, self.prec)
                     wr.deliver_grad(dwk)
                 if x.needs_grad:
                     wt = wr.operand_t()

@@ -51,6 +51,13 @@ int cavp_split_tf32(const float* w, float* hi, float* lo, long long n, void* str
 int cavp_igemm_wgrad(const float* dy, const float* x, float* dw, int nimg, int hs, int ws, int c, int ldx, int ho,
                      int wo, int r, int s, int stride, int pad, int dil, int cout, int lddy, int splits, int prec,
                      void* stream);
+/* Same product with the dY operand pre-split (cavp_split_tf32_2d: dense hi | lo [P][cout], lo = hi + dy_lo_off elements)
+ * and fetched by TMA (128B swizzle with 32-byte atoms = the MN-major tf32 operand layout); the kernel's producer warps
+ * then gather only im2col(x). */
+int cavp_igemm_wgrad_tma(const float* dy_hi, long long dy_lo_off, const float* x, float* dw, int nimg, int hs, int ws,
+                         int c, int ldx, int ho, int wo, int r, int s, int stride, int pad, int dil, int cout,
+                         int splits, int prec, void* stream);
+int cavp_split_tf32_2d(const float* src, int ld, long long rows, int cols, float* hi, float* lo, void* stream);
 
 /* ---- layout / plumbing (csrc/elementwise.cu) -------------------------------------------------------------------- */
 int cavp_zero(void* ptr, long long bytes, void* stream);

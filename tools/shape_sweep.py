@@ -108,9 +108,17 @@ def run_case(case, prec, iters):
         from cavp_b200.engine import Graph
         wsplits = fl.get("splits") or Graph.wgrad_splits(P, ncols, K)  # the engine's choice unless forced
 
-        def fn():
-            _C.call("cavp_igemm_wgrad", _C.ptr(dy), _C.ptr(x), _C.ptr(dw), nimg, h, h, c, c, ho, ho, r, r, stride, pad,
-                    dil, ncols, ncols, wsplits, prec, _C.stream())
+        if Graph.wgrad_via_tma(P, ncols, K):  # as the engine: split dY (timed) + TMA-fed kernel
+            gsp = torch.empty(2, P, ncols, device=dev)
+
+            def fn():
+                _C.call("cavp_split_tf32_2d", _C.ptr(dy), ncols, P, ncols, _C.ptr(gsp[0]), _C.ptr(gsp[1]), _C.stream())
+                _C.call("cavp_igemm_wgrad_tma", _C.ptr(gsp[0]), gsp[0].numel(), _C.ptr(x), _C.ptr(dw), nimg, h, h, c, c,
+                        ho, ho, r, r, stride, pad, dil, ncols, wsplits, prec, _C.stream())
+        else:
+            def fn():
+                _C.call("cavp_igemm_wgrad", _C.ptr(dy), _C.ptr(x), _C.ptr(dw), nimg, h, h, c, c, ho, ho, r, r, stride,
+                        pad, dil, ncols, ncols, wsplits, prec, _C.stream())
         flops = 2.0 * P * ncols * K
     ms = time_it(fn, iters)
     return ms, flops / ms / 1e9
