@@ -178,8 +178,10 @@ def run_ours(args):
     audio_ids = {id(p) for p in audio_params}
     visual_params = [p for p in model.parameters() if id(p) not in audio_ids]
     # main_vpo_mono.py:118-125: SGD(momentum 0.9, wd 5e-4) on the visual groups (lr *= gpus), Adam on the audio backbone
-    opt_v = torch.optim.SGD(visual_params, lr=1e-3 * world, momentum=0.9, weight_decay=5e-4)
-    opt_a = torch.optim.Adam(audio_params, lr=1e-4 * world)
+    # (fused drop-ins of torch.optim.SGD / Adam: cavp_b200/optim.py, one kernel launch per optimiser)
+    from cavp_b200.optim import SGD, Adam
+    opt_v = SGD(visual_params, lr=1e-3 * world, momentum=0.9, weight_decay=5e-4)
+    opt_a = Adam(audio_params, lr=1e-4 * world)
     flat = FlatGradBuffer(list(model.parameters()), dev) if world > 1 else None
 
     image_h, audio_h, pix_h, spl_h = synthetic_batch(B, 666 + rank)
@@ -203,7 +205,7 @@ def run_ours(args):
             flat.all_reduce()
         opt_v.step()
         opt_a.step()
-        launches[0] += res.launches
+        launches[0] += res.launches + 2  # + the two fused optimiser kernels
         if not resident:
             return float(res.l_ce), float(res.l_ctr)  # D2H read of the step's result
         return res

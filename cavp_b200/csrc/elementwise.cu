@@ -92,11 +92,25 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partials, int npart
   const int ch = blockIdx.x * 32 + threadIdx.x;
   double s1 = 0.0, s2 = 0.0;
   if (sums_mode != 2 && ch < C) {
-    for (int i = threadIdx.y; i < nparts; i += 32) {
-      const float* pp = partials + static_cast<size_t>(i) * 2 * ldstat;
-      s1 += pp[ch];
-      s2 += pp[ldstat + ch];
+    // four independent chains: the loop is latency-bound (thousands of partial rows per channel at 112x112), so keep
+    // eight loads in flight per thread instead of two
+    double t1[4] = {0.0, 0.0, 0.0, 0.0}, t2[4] = {0.0, 0.0, 0.0, 0.0};
+    int i = threadIdx.y;
+    for (; i + 96 < nparts; i += 128) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float* pp = partials + static_cast<size_t>(i + 32 * u) * 2 * ldstat;
+        t1[u] += pp[ch];
+        t2[u] += pp[ldstat + ch];
+      }
     }
+    for (; i < nparts; i += 32) {
+      const float* pp = partials + static_cast<size_t>(i) * 2 * ldstat;
+      t1[0] += pp[ch];
+      t2[0] += pp[ldstat + ch];
+    }
+    s1 = (t1[0] + t1[1]) + (t1[2] + t1[3]);
+    s2 = (t2[0] + t2[1]) + (t2[2] + t2[3]);
   }
   sh1[threadIdx.y][threadIdx.x] = s1;
   sh2[threadIdx.y][threadIdx.x] = s2;
@@ -223,8 +237,14 @@ __global__ void partials_sum_kernel(const float* __restrict__ partials, int npar
   double s = 0.0;
   if (i < nk * C) {
     const int k = i / C, ch = i - k * C;
-    for (int pidx = threadIdx.y; pidx < nparts; pidx += 32)
-      s += partials[(static_cast<size_t>(pidx) * nk + k) * ldp + ch];
+    double t[4] = {0.0, 0.0, 0.0, 0.0};
+    int pidx = threadIdx.y;
+    for (; pidx + 96 < nparts; pidx += 128) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) t[u] += partials[(static_cast<size_t>(pidx + 32 * u) * nk + k) * ldp + ch];
+    }
+    for (; pidx < nparts; pidx += 32) t[0] += partials[(static_cast<size_t>(pidx) * nk + k) * ldp + ch];
+    s = (t[0] + t[1]) + (t[2] + t[3]);
   }
   sh[threadIdx.y][threadIdx.x] = s;
   __syncthreads();

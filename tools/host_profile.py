@@ -11,8 +11,9 @@ B = 32
 model = CAVP(50, None, num_classes=bench.CFG["nc"], args=bench.make_args(B, 0, 2), in_plane=1).to(dev).train()
 audio_params = list(model.audio_backbone.backbone.parameters())
 ids = {id(p) for p in audio_params}
-opt_v = torch.optim.SGD([p for p in model.parameters() if id(p) not in ids], lr=1e-3, momentum=0.9, weight_decay=5e-4)
-opt_a = torch.optim.Adam(audio_params, lr=1e-4)
+from cavp_b200.optim import SGD, Adam
+opt_v = SGD([p for p in model.parameters() if id(p) not in ids], lr=1e-3, momentum=0.9, weight_decay=5e-4)
+opt_a = Adam(audio_params, lr=1e-4)
 image, audio, pix, spl = bench.synthetic_batch(B, 666)
 image, audio, pixd = image.to(dev), audio.to(dev), pix.to(dev)
 
@@ -27,6 +28,14 @@ def step():
 
 for _ in range(3):
     step()
+torch.cuda.synchronize()
+# pure host cost: start every step with an empty launch queue
+pure = []
+for _ in range(3):
+    torch.cuda.synchronize()
+    pure.append(step())
+print("issue ms per step with an EMPTY queue: train_step", [round(1e3 * a, 1) for a, b in pure], "optim",
+      [round(1e3 * b, 1) for a, b in pure])
 torch.cuda.synchronize()
 torch.cuda.set_sync_debug_mode("warn")
 ts = [step() for _ in range(4)]
