@@ -265,14 +265,26 @@ def run_ours(args):
             with open(args.dump_profile, "w") as f:
                 for ms_, name, tag, fl in rows_[:150]:
                     f.write(f"{ms_:8.3f} ms  {fl / ms_ / 1e9 if ms_ > 0 else 0:7.1f} TF  {name}  {tag}\n")
-        ig_ms = agg.get("cavp_igemm", [0, 0, 0, 0])[0] + agg.get("cavp_igemm_wgrad", [0, 0, 0, 0])[0]
-        ig_fl = agg.get("cavp_igemm", [0, 0, 0, 0])[2] + agg.get("cavp_igemm_wgrad", [0, 0, 0, 0])[2]
-        ig_n = agg.get("cavp_igemm", [0, 0, 0, 0])[1] + agg.get("cavp_igemm_wgrad", [0, 0, 0, 0])[1]
+        ig = [agg.get(k, [0, 0, 0, 0]) for k in ("cavp_igemm", "cavp_igemm_wgrad", "cavp_igemm_wgrad_tma")]
+        ig_ms, ig_n, ig_fl = sum(v[0] for v in ig), sum(v[1] for v in ig), sum(v[2] for v in ig)
+        # DRAM traffic per launch of the same kernels, from the committed ncu launch list of this command
+        # (profiles/r01_ncu_step_summary.json, written by tools/ncu_summarize.py; ncu counters cannot be read live)
+        traffic, traffic_src = None, None
+        try:
+            summ = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_step_summary.json")))["kernels"]
+            ig = [v for k, v in summ.items() if "igemm" in k]
+            n_l = sum(v["launches"] for v in ig)
+            if n_l:
+                traffic = 1e6 * sum(v["dram_read_MB"] + v["dram_write_MB"] for v in ig) / n_l
+                traffic_src = ("profiles/r01_ncu_step_summary.json: dram__bytes_read.sum + dram__bytes_write.sum over "
+                               f"{n_l} igemm launches of the bench command, bytes per launch")
+        except Exception:
+            pass
         peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
         achieved = ig_fl / (ig_ms / 1e3) / 1e12 if ig_ms else 0.0
-        roofline = {"bound": "tensor", "kernel": "igemm_kernel<BN,PREC,MODE> (cavp_igemm + cavp_igemm_wgrad)",
+        roofline = {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM tile kernels igemm_ws / igemm_ws2 / igemm_kernel (cavp_igemm + cavp_igemm_wgrad[_tma])",
                     "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                    "traffic": None, "launches_per_step": ig_n, "avg_launch_ms": ig_ms / max(ig_n, 1),
+                    "traffic": traffic, "traffic_source": traffic_src, "launches_per_step": ig_n, "avg_launch_ms": ig_ms / max(ig_n, 1),
                     "flop_per_step_executed": ig_fl, "share_of_kernel_time": ig_ms / total_ms if total_ms else None,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (measured)" if peaks else "fallback",
                     "note": "fp32-parity mode issues 3 TF32 MMAs per product (<= 1/6 of the bf16 peak by construction)"}

@@ -58,6 +58,37 @@ __device__ __forceinline__ float act_bwd_from_out(float z, int act, float slope)
   return 1.f;
 }
 
+// Source index exactly as ATen's area_pixel_compute_source_index (fp32 arithmetic).
+struct Lerp { int i0, i1; float w0, w1; };
+__device__ __forceinline__ Lerp lerp_index(int dst, int in_size, float scale, int align_corners) {
+  float src;
+  if (align_corners) {
+    src = scale * dst;
+  } else {
+    src = scale * (dst + 0.5f) - 0.5f;
+    if (src < 0.f) src = 0.f;
+  }
+  Lerp l;
+  l.i0 = static_cast<int>(src);
+  if (l.i0 > in_size - 1) l.i0 = in_size - 1;
+  l.i1 = l.i0 + (l.i0 < in_size - 1 ? 1 : 0);
+  l.w1 = src - l.i0;
+  l.w0 = 1.f - l.w1;
+  return l;
+}
+__host__ __device__ inline float lerp_scale(int in_size, int out_size, int align_corners) {
+  if (align_corners) return out_size > 1 ? static_cast<float>(in_size - 1) / (out_size - 1) : 0.f;
+  return static_cast<float>(in_size) / out_size;
+}
+
+// One fixed evaluation order (explicit fma / mul), shared by the full-resolution upsample and by the fused
+// upsample + argmax of the eval epilogue, so that both see bit-identical logits.
+__device__ __forceinline__ float bilerp(const Lerp& ly, const Lerp& lx, float a, float b, float c, float d) {
+  const float top = __fmaf_rn(lx.w0, a, __fmul_rn(lx.w1, b));
+  const float bot = __fmaf_rn(lx.w0, c, __fmul_rn(lx.w1, d));
+  return __fmaf_rn(ly.w0, top, __fmul_rn(ly.w1, bot));
+}
+
 inline int grid_for(long long work_items, int per_block, int max_waves = 8) {
   long long b = (work_items + per_block - 1) / per_block;
   const long long cap = static_cast<long long>(NUM_SMS) * max_waves;

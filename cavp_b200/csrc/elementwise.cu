@@ -390,29 +390,6 @@ __global__ void pixel_bcast_kernel(const float* __restrict__ dout, float* __rest
 }
 
 // ------------------------------------------------------------------------------------------------ bilinear
-// Source index exactly as ATen's area_pixel_compute_source_index (fp32 arithmetic).
-struct Lerp { int i0, i1; float w0, w1; };
-__device__ __forceinline__ Lerp lerp_index(int dst, int in_size, float scale, int align_corners) {
-  float src;
-  if (align_corners) {
-    src = scale * dst;
-  } else {
-    src = scale * (dst + 0.5f) - 0.5f;
-    if (src < 0.f) src = 0.f;
-  }
-  Lerp l;
-  l.i0 = static_cast<int>(src);
-  if (l.i0 > in_size - 1) l.i0 = in_size - 1;
-  l.i1 = l.i0 + (l.i0 < in_size - 1 ? 1 : 0);
-  l.w1 = src - l.i0;
-  l.w0 = 1.f - l.w1;
-  return l;
-}
-__host__ __device__ inline float lerp_scale(int in_size, int out_size, int align_corners) {
-  if (align_corners) return out_size > 1 ? static_cast<float>(in_size - 1) / (out_size - 1) : 0.f;
-  return static_cast<float>(in_size) / out_size;
-}
-
 __global__ void bilinear_fwd_nhwc_kernel(const float* __restrict__ x, int ldx, int hin, int win,
                                          float* __restrict__ y, int ldy, int hout, int wout, int n, int C4,
                                          int align, float sh, float sw) {
@@ -457,7 +434,7 @@ __global__ void bilinear_fwd_nchw_kernel(const float* __restrict__ x, int ldx, i
     const float* pd = base + (static_cast<long long>(ly.i1) * win + lx.i1) * ldx;
     float* o = y + img * C * plane + static_cast<long long>(oy) * wout + ox;
     for (int ch = 0; ch < C; ++ch)
-      o[ch * plane] = ly.w0 * (lx.w0 * pa[ch] + lx.w1 * pb[ch]) + ly.w1 * (lx.w0 * pc[ch] + lx.w1 * pd[ch]);
+      o[ch * plane] = bilerp(ly, lx, pa[ch], pb[ch], pc[ch], pd[ch]);
   }
 }
 // Gather-form backward (deterministic, no atomics): every low-res element collects from the output pixels whose

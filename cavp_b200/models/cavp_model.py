@@ -477,6 +477,7 @@ class CAVP(nn.Module):
         self.memory = SoundBank(out_dim=self.latent_dim, args=args, device=args.local_rank)
         self.local_rank = args.local_rank
         self.num_classes = num_classes
+        self.ignore_index = ignore_index
         self.in_plane = in_plane
         self.audio_kind = "vgg" if args.audio_backbone == "vgg" else "resnet18"
         self.prec = int(getattr(args, "cavp_prec", 2))  # 2 = fp32-parity (3xTF32 + promotion), 1 = plain TF32
@@ -551,6 +552,29 @@ class CAVP(nn.Module):
             pred = g.upsample_to_nchw(logits, self.num_classes, image.shape[-2], image.shape[-1])
             self.last_launches = g.launches
         return pred, fusion.nchw(), _pack(fusion.n, proj, fea_a, attn)
+
+    def forward_eval_metrics(self, image, audio, target, conf=None, ignore_index=None, want_pred=True):
+        """forward_inference + the metric epilogue of trainer.validation (trainer_cavp_vpo_mono.py:272-277:
+        `MIoU(logits, label)`, `ForegroundDetect(logits, label)`) without ever writing the full-resolution logits: the
+        bilinear upsample of forward_cls, the argmax and the (label, prediction) confusion counts run in one kernel.
+        Returns (pred int64 [B,H,W] or None, conf int64 [(nc+1), nc]); pass `conf` back in to accumulate over a
+        validation epoch and hand it to cavp_b200.metrics.MIoU / ForegroundDetect `.update_from_confusion`."""
+        if not image.is_cuda:
+            raise RuntimeError("cavp_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+        nc = self.num_classes
+        with torch.no_grad():
+            g = Graph(image.device, prec=self.prec, train=False)
+            logits, fusion, proj, fea_a, attn = self.build_graph(g, image, audio)
+            H, W = image.shape[-2:]
+            if conf is None:
+                conf = torch.zeros(nc + 1, nc, dtype=torch.int64, device=image.device)
+            labels = target.reshape(logits.n, H, W).to(image.device, torch.int64).contiguous()
+            pred = torch.empty(logits.n, H, W, dtype=torch.int64, device=image.device) if want_pred else None
+            g.call("cavp_upsample_argmax_confusion", logits.ptr, logits.ld, logits.h, logits.w, H, W, logits.n, nc,
+                   labels.data_ptr(), self.ignore_index if ignore_index is None else ignore_index,
+                   0 if pred is None else pred.data_ptr(), conf.data_ptr())
+            self.last_launches = g.launches
+        return pred, conf
 
     def forward(self, image, audio=None, shuffle_info=None, ow_flag=False, eval_mode=False, audio_func=False):
         if eval_mode:

@@ -166,6 +166,20 @@ int cavp_sgd_multi(const void* table, const int* work, int nwork, float momentum
 int cavp_adam_multi(const void* table, const int* work, int nwork, double beta1, double beta2, double eps,
                     double bias_correction1, double bias_correction2, void* stream);
 
+/* ---- eval epilogue (csrc/metrics.cu) -----------------------------------------------------------
+ * Replace torch.max(logits, 1) + 3x torch.histc (utils/eval_utils.py:73-97, MIoU) and argmax -> .cpu().numpy() ->
+ * numpy.bincount (utils/eval_utils.py:107-117,151-155, ForegroundDetect) with one pass: pred[b][px] = first argmax over
+ * the C classes and conf[(C+1)][C] += 1 at (label, pred); label == ignore_index or < 0 is skipped, label >= C counts in
+ * row C.  conf accumulates (zero it once per evaluation).  pred / labels / conf may each be NULL (labels and conf go
+ * together).  cavp_upsample_argmax_confusion takes the LOW-resolution NHWC logits of forward_cls and applies the bilinear
+ * upsample of models/cavp_model.py:140 (align_corners=False) on the fly with the arithmetic of cavp_bilinear_fwd, so the
+ * full-resolution logits are never written. */
+int cavp_argmax_confusion(const float* logits, const long long* labels, int B, int C, long long HW, int ignore_index,
+                          long long* pred, unsigned long long* conf, void* stream);
+int cavp_upsample_argmax_confusion(const float* x, int ldx, int hin, int win, int hout, int wout, int n, int C,
+                                   const long long* labels, int ignore_index, long long* pred, unsigned long long* conf,
+                                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif
