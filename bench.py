@@ -165,7 +165,9 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("CAVP_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+        # keep stdout to the one JSON line: NCCL prints its version banner (and any INFO the box configures) to stdout
+        os.environ["NCCL_DEBUG"] = os.environ.get("CAVP_NCCL_DEBUG", "WARN")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     torch.manual_seed(666 + rank)  # main_*.py: seed_it(seed + local_rank), seed 666
