@@ -382,6 +382,17 @@ class Graph:
             self.work(nbytes=8.0 * M * co)
             self.call("cavp_gelu_fwd", tgt.ptr, y.ptr, M * co)
             assert stats is None
+        elif (res is not None and res.ptr != y.ptr and not res_div and act == ACT_NONE and pre is None
+              and stats is None and M >= 65536):
+            # large GEMM + residual: the persistent / pair kernels with the plain epilogue, then one HBM-bound add
+            # (a residual fetched inside the epilogue serialises four exposed global-latency waits per tile)
+            self._igemm(x, wr.operand(), co, K, y, geom=geom, shift=bias_t)
+            reps = 1 if res_mod == 0 else M // res_mod
+            nrows = M // reps
+            for i in range(reps):
+                part = Act(y.buf[i * nrows:(i + 1) * nrows], 1, 1, nrows, y.c, y.off)
+                rpart = Act(res.buf[:nrows], 1, 1, nrows, res.c, res.off)
+                self.add_act(part, rpart)
         else:
             self._igemm(x, wr.operand(), co, K, y, geom=geom, y_pre=pre, shift=bias_t, res=res, res_mod=res_mod,
                         res_div=res_div, stats_ptr=0 if stats is None else stats[1],

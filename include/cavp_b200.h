@@ -180,6 +180,19 @@ int cavp_upsample_argmax_confusion(const float* x, int ldx, int hin, int win, in
                                    const long long* labels, int ignore_index, long long* pred, unsigned long long* conf,
                                    void* stream);
 
+/* ---- audio front-end (csrc/audio.cu) -------------------------------------------------------------
+ * Replace CAVP_TRAINER.preprocess_audio (trainer/trainer_cavp_vpo_mono.py:43-53,61-71): torchaudio MelSpectrogram
+ * (n_fft 512, win 400, hop 160, 64 mels, 125-3800 Hz, power 2, center / reflect) -> first T frames -> transpose ->
+ * 20*log10(max(1e-5, x)) -> 2*(x - spec_min)/(spec_max - spec_min) - 1 (utils/sourcesep.py:23-47).
+ * cavp_mel_frames: frames[(r*T + t)][j] = window[j] * reflect_pad(wave_r, n_fft/2)[t*hop + j]  (window already padded
+ *   to n_fft).  The real DFT is then ONE cavp_igemm against the constant [2*(n_fft/2+1)][n_fft] cos | -sin basis.
+ * cavp_mel_power_db: spec rows hold Re[0..nf) | Im[nf..2nf); out[frame][m] = norm(db_scale*log10(max(amin, sum_k
+ *   (Re_k^2 + Im_k^2) * fb[k][m]))), written as [rows][T][n_mels]. */
+int cavp_mel_frames(const float* wave, long long ldw, int A, int rows, int T, int n_fft, int hop, const float* window,
+                    float* frames, void* stream);
+int cavp_mel_power_db(const float* spec, int lds, int nf, const float* fb, int n_mels, long long frames, float amin,
+                      float db_scale, float spec_min, float spec_max, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
