@@ -1,0 +1,69 @@
+"""BASELINE.json configs[2..4] at FULL size on one B200 (per-GPU shard of each config): one train step through the C-ABI
+kernels, checked through properties that do not need a CPU oracle at that size:
+
+  * losses and every gradient finite, logits not degenerate;
+  * the CE kernel agrees with torch's cross_entropy evaluated on the RETURNED full-resolution logits (an independent
+    check of the loss path at 32 x nc x 224^2);
+  * `output_cat[B:]` (the zero-weighted shuffled half) is still produced (the reference returns it);
+  * the eval epilogue on the same weights: fused upsample+argmax == argmax of the materialised logits.
+
+cfg 2 (AVSS): 71 classes, dilation FFF, VGG audio, bs32.  cfg 3 (VPO-MS, "5-frame clips"): T folded into the batch,
+16 x 5 = 80 images.  cfg 4 (VPO-MSMI stereo): ResNet-18 audio on [32, 2, 300, 64], audio_func=True.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from test_parity_gpu import build_model
+from oracle import seeded
+
+pytestmark = pytest.mark.gpu
+
+CONFIGS = {
+    "cfg2_avss_fff71_bs32": dict(B=32, H=224, W=224, nc=71, dilation=(False, False, False), audio="vgg", in_plane=1,
+                                 frames=96, audio_func=False),
+    "cfg3_vpo_ms_t5_bs80": dict(B=80, H=224, W=224, nc=22, dilation=(False, True, True), audio="vgg", in_plane=1,
+                                frames=96, audio_func=False),
+    "cfg4_msmi_stereo_r18_bs32": dict(B=32, H=224, W=224, nc=22, dilation=(False, True, True), audio="18", in_plane=2,
+                                      frames=300, audio_func=True),
+}
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_full_size_config_step(name):
+    from cavp_b200.trainer import shuffled_labels, train_step
+    cfg = CONFIGS[name]
+    B = cfg["B"]
+    model = build_model(cfg).train()
+    batch = seeded.synthetic_batch(B, cfg["H"], cfg["W"], cfg["nc"], seed=666, audio_frames=cfg["frames"],
+                                   in_plane=cfg["in_plane"])
+    spl = shuffled_labels(batch["pix_label"], batch["img_label"], batch["shuffle_idx"])
+    audio = batch["audio"][:B] if cfg["audio_func"] else batch["audio"]
+    torch.manual_seed(1234)
+    res = train_step(model, batch["image"].cuda(), audio.cuda(), batch["pix_label"], spl, max_views=512,
+                     shuffle_idx=batch["shuffle_idx"].cuda() if cfg["audio_func"] else None,
+                     audio_func=cfg["audio_func"], keep_outputs=True)
+    torch.cuda.synchronize()
+    assert res.out_pred.shape == (2 * B, cfg["nc"], cfg["H"], cfg["W"])
+    assert torch.isfinite(res.l_ce) and torch.isfinite(res.l_ctr) and float(res.l_ce) > 0
+    labels = batch["pix_label"].cuda()
+    ce_ref = F.cross_entropy(res.out_pred[:B].double(), labels, ignore_index=255)
+    assert abs(float(res.l_ce) - float(ce_ref)) < 1e-5 * float(ce_ref)
+    assert float(res.out_pred[B:].abs().max()) > 0                       # the shuffled half is materialised too
+    n_grads = 0
+    for n, p in model.named_parameters():
+        if n.startswith("cross_att.pos_embed") or n.startswith("audio_backbone.cls_head"):
+            continue                                                      # never receive gradients in the reference either
+        assert p.grad is not None and torch.isfinite(p.grad).all(), n
+        n_grads += 1
+    assert n_grads > 150
+    # eval epilogue at full size on the first 8 images
+    model.eval()
+    img, aud, lab = batch["image"][:8].cuda(), audio[:8].cuda(), labels[:8]
+    with torch.no_grad():
+        pred_full, _, _ = model(img, aud, eval_mode=True)
+    pred, conf = model.forward_eval_metrics(img, aud, lab)
+    assert torch.equal(pred, pred_full.argmax(1))
+    assert int(conf.sum()) == int((lab != 255).sum())
+    del res
+    torch.cuda.empty_cache()
