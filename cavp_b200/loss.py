@@ -218,3 +218,96 @@ class Losser(nn.Module):
 
     def forward(self, output, pix_label, pack_=None):
         return self.loss_ce(output, pix_label)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# AVContrast (loss/av_contrast.py) - SURVEY.md 8(f) N4.  Dead code in the reference (constructed in loss/losser.py:57,
+# never called by a trainer); provided because BASELINE.json's north_star names it.
+def avcontrast_host_labels(labels, ignore_label=255, size=128):
+    """Host-side index logic of AVContrast.forward / _contrastive on the label map (loss/av_contrast.py:27-40,97-106):
+    nearest resize to 128 x 128 (F.interpolate(mode="nearest") index rule: src = floor(dst * in / out)), foreground mask
+    (label != 0 and != ignore), per-image foreground class (-1 = none).  The reference's torch.stack(batch_target) only
+    works when every image has at most one foreground class; more raises here as it does there."""
+    lab = labels.detach().cpu()
+    b, H, W = lab.shape
+    iy = torch.div(torch.arange(size) * H, size, rounding_mode="floor").clamp_(max=H - 1)
+    ix = torch.div(torch.arange(size) * W, size, rounding_mode="floor").clamp_(max=W - 1)
+    small = lab[:, iy][:, :, ix].reshape(b, size * size)
+    mask = ((small != 0) & (small != ignore_label))
+    target = torch.full((b,), -1, dtype=torch.int32)
+    for i in range(b):
+        u = torch.unique(small[i])
+        u = u[(u != ignore_label) & (u != 0)]
+        if len(u) > 1:
+            raise ValueError("AVContrast: more than one foreground class in an image (the reference's torch.stack of "
+                             "per-image unique labels fails on this input too)")
+        if len(u) == 1:
+            target[i] = int(u[0])
+    return mask.to(torch.uint8), mask.sum(1).float(), target
+
+
+class _AVContrastFn(torch.autograd.Function):
+    NCHUNK = 64
+
+    @staticmethod
+    def forward(ctx, f_v, f_a, mask, cnt, target, temperature, eps):
+        b, hw, c = f_v.shape
+        dev = f_v.device
+        st = torch.cuda.current_stream(dev).cuda_stream
+        fv = f_v.detach().float().contiguous()
+        fa = f_a.detach().float().contiguous()
+        nch = _AVContrastFn.NCHUNK
+        partials = torch.empty(b, nch, 2, c, device=dev)
+        _C.call("cavp_avc_colstats", fv.data_ptr(), mask.data_ptr(), b, hw, c, nch, partials.data_ptr(), st)
+        feats = torch.empty(2 * b, c, device=dev)
+        dfeat = torch.empty(2 * b, c, device=dev)
+        nrm, msum = torch.empty(b, c, device=dev), torch.empty(b, c, device=dev)
+        loss = torch.empty(1, device=dev)
+        d_fa, dms, dnn = torch.empty(b, c, device=dev), torch.empty(b, c, device=dev), torch.empty(b, c, device=dev)
+        _C.call("cavp_avc_loss", partials.data_ptr(), nch, b, c, fa.data_ptr(), cnt.data_ptr(), target.data_ptr(),
+                float(temperature), float(eps), feats.data_ptr(), dfeat.data_ptr(), nrm.data_ptr(), msum.data_ptr(),
+                loss.data_ptr(), d_fa.data_ptr(), dms.data_ptr(), dnn.data_ptr(), st)
+        ctx.save_for_backward(fv, mask, d_fa, dms, dnn)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        fv, mask, d_fa, dms, dnn = ctx.saved_tensors
+        b, hw, c = fv.shape
+        st = torch.cuda.current_stream(fv.device).cuda_stream
+        gs = g.detach().float().reshape(1).contiguous()
+        dfv = torch.empty_like(fv)
+        _C.call("cavp_avc_bwd", fv.data_ptr(), mask.data_ptr(), dms.data_ptr(), dnn.data_ptr(), gs.data_ptr(), b, hw, c,
+                dfv.data_ptr(), st)
+        dfa = torch.empty_like(d_fa)
+        # d_fa * g: a [b, c] rescale on the same kernel family (bn_apply: out = y*scale + shift with scale = g)
+        scale = gs.expand(c).contiguous()            # keep both alive until the launch is enqueued
+        shift = torch.zeros(c, device=fv.device)
+        _C.call("cavp_bn_apply", d_fa.data_ptr(), c, scale.data_ptr(), shift.data_ptr(), 0, 0, dfa.data_ptr(), c, b, c, 0,
+                0.0, st)
+        return dfv, dfa, None, None, None, None, None
+
+
+class AVContrast(nn.Module):
+    """loss/av_contrast.py:8-112: same constructor (temp1, local_rank) and forward(f_v [b, hw, c], f_a [b, c], labels
+    [b, H, W]); hw must be 128*128 as in the reference (:89 hard-codes h, w = 128)."""
+
+    def __init__(self, temp1, local_rank=0):
+        super().__init__()
+        self.temperature = temp1
+        self.base_temperature = self.temperature
+        self.ignore_label = 255
+        self.eps = 1e-12
+        self.local_rank = local_rank
+
+    def forward(self, f_v, f_a, labels=None):
+        if not f_v.is_cuda:
+            raise RuntimeError("cavp_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+        b, hw, c = f_v.shape
+        if hw != 128 * 128:
+            raise ValueError("AVContrast expects a 128 x 128 token map (loss/av_contrast.py:89)")
+        if c % 4:
+            raise ValueError("channel count must be a multiple of 4")
+        mask, cnt, target = avcontrast_host_labels(labels, self.ignore_label)
+        dev = f_v.device
+        return _AVContrastFn.apply(f_v, f_a, mask.to(dev), cnt.to(dev), target.to(dev), self.temperature, self.eps)

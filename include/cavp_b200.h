@@ -193,6 +193,20 @@ int cavp_mel_frames(const float* wave, long long ldw, int A, int rows, int T, in
 int cavp_mel_power_db(const float* spec, int lds, int nf, const float* fb, int n_mels, long long frames, float amin,
                       float db_scale, float spec_min, float spec_max, float* out, void* stream);
 
+/* ---- AVContrast (csrc/avcontrast.cu; loss/av_contrast.py:20-112) --------------------------------
+ * f_v [b][hw][c] normalised over hw, masked-average-pooled over the foreground pixels (mask: uint8 [b][hw] from the
+ * 128x128 nearest-resized labels), contrasted with the normalised audio vectors f_a [b][c]; target[i] = the image's
+ * foreground class or -1.  cavp_avc_colstats: partials [b][nchunk][2][c] (sum f^2, sum mask*f).  cavp_avc_loss: loss[0]
+ * and, for a unit upstream gradient, d_fa [b][c] plus the coefficients dms / dnn [b][c] of
+ * cavp_avc_bwd: dfv = g * (mask * dms + f_v * dnn)  (gscale: device scalar or NULL = 1). */
+int cavp_avc_colstats(const float* fv, const unsigned char* mask, int b, int hw, int c, int nchunk, float* partials,
+                      void* stream);
+int cavp_avc_loss(const float* partials, int nchunk, int b, int c, const float* fa, const float* cnt, const int* target,
+                  float temperature, float eps, float* feats, float* dfeat, float* nrm, float* msum, float* loss,
+                  float* d_fa, float* dms, float* dnn, void* stream);
+int cavp_avc_bwd(const float* fv, const unsigned char* mask, const float* dms, const float* dnn, const float* gscale,
+                 int b, int hw, int c, float* dfv, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
