@@ -151,18 +151,27 @@ static int dispatch(IgemmParams& p, int prec, long long b_lo_off, cudaStream_t s
       // Schedule choice, measured per shape at PREC=2 (profiles/r01_shape_sweep_sched.txt):
       //  * the persistent kernel (ws) beats the one-tile-per-CTA kernel by 5-30 % (its epilogue overlaps the next tile's
       //    main loop; short-K GEMMs gain most) except when the epilogue fetches a residual or evaluates erf/exp;
-      //  * the CTA-pair kernel (ws2) adds ~5 % on top when there are enough 256-row pair tiles to keep all 74 TPCs busy
-      //    (each SM reads only half of the weight tile from shared memory).
+      //  * the CTA-pair kernel (ws2) adds 5-15 % on top when there are enough 256-row pair tiles to keep all 74 TPCs
+      //    busy (each SM reads only half of the weight tile from shared memory); with 160-column tiles where they pad N
+      //    less than 128-column tiles (N = 304: +35 %) or barely more on long-K GEMMs (N = 2048, K >= 1024: +13 %).
       // CAVP_IGEMM_WS=0/1/2 forces tile / ws / pair.
       const int m_tiles_ = (p.M + BM - 1) / BM;
       const bool heavy_epilogue = (p.res != nullptr && !igemm_inplace_acc(p)) || p.act == ACT_GELU || p.act == ACT_SIGMOID;
-      int sched = prec == 1 ? 1 : (heavy_epilogue ? 0 : ((bn == 128 && m_tiles_ >= 512) ? 2 : 1));
+      int sched = prec == 1 ? 1 : (heavy_epilogue ? 0 : ((bn == 128 && m_tiles_ >= 148) ? 2 : 1));
       if (ws_env) sched = ws_env[0] - '0';
       if (sched == 2 && bn == 128) {  // CTA-pair kernel: each CTA fetches half of the weight rows
-        rc = make_weight_tmap(&tm_hi, p.w, p.Ncols, p.K, p.ldw, bn / 2);
+        // 160-column tiles when they pad N less than 128-column tiles do (N = 304: 2 x 160 = 320 instead of 3 x 128 = 384)
+        static const char* bn_env = getenv("CAVP_IGEMM_BN160");
+        const int pad128 = (p.Ncols + 127) / 128 * 128, pad160 = (p.Ncols + 159) / 160 * 160;
+        const bool bn160 = prec == 2 && (bn_env ? bn_env[0] != '0'
+                                                : (pad160 < pad128 || (pad160 * 100 <= pad128 * 102 && p.num_kb >= 32)));
+        const int pbn = bn160 ? 160 : 128;
+        p.n_tiles = (p.Ncols + pbn - 1) / pbn;
+        rc = make_weight_tmap(&tm_hi, p.w, p.Ncols, p.K, p.ldw, pbn / 2);
         if (rc) return rc;
-        rc = make_weight_tmap(&tm_lo, p.w + b_lo_off, p.Ncols, p.K, p.ldw, bn / 2);
+        rc = make_weight_tmap(&tm_lo, p.w + b_lo_off, p.Ncols, p.K, p.ldw, pbn / 2);
         if (rc) return rc;
+        if (bn160) return launch_igemm_ws2<160, 2>(p, tm_hi, tm_lo, st);
         return prec == 2 ? launch_igemm_ws2<128, 2>(p, tm_hi, tm_lo, st) : launch_igemm_ws2<128, 1>(p, tm_hi, tm_lo, st);
       }
       const bool use_ws = sched >= 1;

@@ -23,12 +23,12 @@ namespace cavp {
 template <int BN, int PREC>
 struct Ws2Cfg {
   static constexpr bool PROMOTE = (PREC == 2);
-  static constexpr int NBUF = 512 / BN >= 4 ? 4 : 512 / BN;
+  static constexpr int NBUF = 512 / BN >= 4 ? 4 : 512 / BN;  // BN = 160: three 160-column accumulators
   static constexpr int BH = BN / 2;  // weight rows held by one CTA
   static constexpr int A_BYTES = BM * 128;
   static constexpr int B_BYTES = BH * 128;
   static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * PREC;
-  static constexpr int STAGES = (PREC == 2) ? 4 : 6;
+  static constexpr int STAGES = (PREC == 2) ? (BN > 128 ? 3 : 4) : 6;
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
   static constexpr int BAR_BYTES = 256;
   static constexpr int ROWTAB_BYTES = BM * 8;
@@ -62,7 +62,7 @@ igemm_ws2_kernel(const IgemmParams p, const __grid_constant__ CUtensorMap tm_b_h
   using Cfg = Ws2Cfg<BN, PREC>;
   constexpr bool PROMOTE = Cfg::PROMOTE;
   constexpr int NBUF = Cfg::NBUF;
-  static_assert(BN == 128, "pair kernel: 128-column tiles (64 weight rows per CTA)");
+  static_assert(BN == 128 || BN == 160, "pair kernel: 128- or 160-column tiles (64 / 80 weight rows per CTA)");
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -121,15 +121,25 @@ igemm_ws2_kernel(const IgemmParams p, const __grid_constant__ CUtensorMap tm_b_h
       for (int j = 0; j < BN; ++j) acc[j] = 0.f;
       for (int u = 0; u < nunits; ++u) {
         const int U = ubase + u;
-        const int b = U & (NBUF - 1);
+        const int b = U % NBUF;
         mbar_wait(&accf_bar[b], (U / NBUF) & 1);
         tc_fence_after();
+        if constexpr (BN > 128) {  // 160 accumulators per thread: 16-column loads keep the temporaries small
 #pragma unroll
-        for (int cg = 0; cg < BN / 32; ++cg) {
-          float v[32];
-          tmem_ld32(tmem_base + lane_base + static_cast<uint32_t>(b * BN + cg * 32), v);
+          for (int cg = 0; cg < BN / 16; ++cg) {
+            float v[16];
+            tmem_ld16(tmem_base + lane_base + static_cast<uint32_t>(b * BN + cg * 16), v);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) acc[cg * 32 + j] += v[j];
+            for (int j = 0; j < 16; ++j) acc[cg * 16 + j] += v[j];
+          }
+        } else {
+#pragma unroll
+          for (int cg = 0; cg < BN / 32; ++cg) {
+            float v[32];
+            tmem_ld32(tmem_base + lane_base + static_cast<uint32_t>(b * BN + cg * 32), v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[cg * 32 + j] += v[j];
+          }
         }
         tc_fence_before();
         __syncwarp();
@@ -286,7 +296,7 @@ igemm_ws2_kernel(const IgemmParams p, const __grid_constant__ CUtensorMap tm_b_h
           const int G = gbase + it;
           const int s = G % Cfg::STAGES;
           const int U = ubase + (PROMOTE ? (it >> 1) : 0);
-          const int b = U & (NBUF - 1);
+          const int b = U % NBUF;
           const bool unit_first = PROMOTE ? ((it & 1) == 0) : (it == 0);
           const bool unit_last = PROMOTE ? ((it & 1) == 1 || it == wk.nkb - 1) : (it == wk.nkb - 1);
           if (unit_first) {

@@ -63,7 +63,12 @@ def test_full_size_config_step(name):
     with torch.no_grad():
         pred_full, _, _ = model(img, aud, eval_mode=True)
     pred, conf = model.forward_eval_metrics(img, aud, lab)
-    assert torch.equal(pred, pred_full.argmax(1))
+    # two separate forward passes: split-K layers accumulate with red.global.add (order not fixed), so the logits of
+    # the two passes agree to fp32 rounding, not bitwise - the argmax must agree wherever the top-2 margin is not noise
+    top2 = pred_full.topk(2, dim=1).values
+    safe = (top2[:, 0] - top2[:, 1]) > 1e-4 * float(pred_full.abs().max())
+    assert torch.equal(pred[safe], pred_full.argmax(1)[safe])
+    assert float((pred != pred_full.argmax(1)).float().mean()) < 1e-3
     assert int(conf.sum()) == int((lab != 255).sum())
     del res
     torch.cuda.empty_cache()

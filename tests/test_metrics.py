@@ -127,7 +127,23 @@ def test_fused_upsample_argmax_equals_materialised_path():
     with torch.no_grad():
         out_pred, _, _ = model(image, audio, eval_mode=True)
     pred_ref, conf_ref = argmax_confusion(out_pred, target, 255, want_pred=True)
-    pred, conf = model.forward_eval_metrics(image, audio, target)
-    assert torch.equal(pred, pred_ref)
-    assert torch.equal(conf, conf_ref)
     assert torch.equal(pred_ref.cpu(), out_pred.cpu().argmax(1))
+    pred, conf = model.forward_eval_metrics(image, audio, target)
+    # (a second forward pass: split-K layers accumulate with red.global.add, so its logits equal the first pass's to
+    # fp32 rounding, not bitwise; the fused kernel itself is checked bit-exactly below on the SAME low-resolution logits)
+    top2 = out_pred.topk(2, dim=1).values
+    safe = (top2[:, 0] - top2[:, 1]) > 1e-4 * float(out_pred.abs().max())
+    assert torch.equal(pred[safe], pred_ref[safe])
+    assert int((conf - conf_ref).abs().sum()) <= 2 * int((~safe).sum())
+    # same logits, both kernels: upsample with cavp_bilinear_fwd then argmax  ==  fused upsample+argmax
+    from cavp_b200 import _C
+    low = torch.randn(2, 16, 24, 24, device="cuda")                      # NHWC [n, h, w, C=24 (22 used)]
+    full = torch.empty(2, nc, 64, 96, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    _C.call("cavp_bilinear_fwd", low.data_ptr(), 24, 16, 24, full.data_ptr(), 0, 64, 96, 2, nc, 0, 1, st)
+    p_mat, c_mat = argmax_confusion(full, target, 255, want_pred=True)
+    p_fused = torch.empty(2, 64, 96, dtype=torch.int64, device="cuda")
+    c_fused = torch.zeros(nc + 1, nc, dtype=torch.int64, device="cuda")
+    _C.call("cavp_upsample_argmax_confusion", low.data_ptr(), 24, 16, 24, 64, 96, 2, nc, target.data_ptr(), 255,
+            p_fused.data_ptr(), c_fused.data_ptr(), st)
+    assert torch.equal(p_fused, p_mat) and torch.equal(c_fused, c_mat)
