@@ -5,6 +5,7 @@
 #include "igemm_ts.cuh"
 #include "igemm_ws.cuh"
 #include "igemm_ws2.cuh"
+#include "igemm_wgrad2.cuh"
 #include "../../include/cavp_b200.h"
 
 namespace cavp {
@@ -131,6 +132,23 @@ static int launch_igemm_ws2(const IgemmParams& p, const CUtensorMap& tm_hi, cons
   return static_cast<int>(cudaGetLastError());
 }
 
+template <int PREC>
+static int launch_wgrad2(const IgemmParams& p, const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, cudaStream_t st) {
+  using Cfg = Wg2Cfg<PREC>;
+  auto kern = igemm_wgrad2_kernel<PREC>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    configured = true;
+  }
+  const int m_tiles = (p.M + BM - 1) / BM;
+  const int m_pairs = (m_tiles + 1) / 2;
+  dim3 grid(static_cast<unsigned>(2 * m_pairs * p.n_tiles), static_cast<unsigned>(p.splits), 1);
+  kern<<<grid, CTA_THREADS, Cfg::SMEM_BYTES, st>>>(p, tm_hi, tm_lo);
+  return static_cast<int>(cudaGetLastError());
+}
+
 // b_lo_off > 0: the B operand is pre-split ([hi | lo], lo at w + b_lo_off) and is fetched by TMA
 template <int MODE>
 static int dispatch(IgemmParams& p, int prec, long long b_lo_off, cudaStream_t st) {
@@ -199,6 +217,11 @@ static int dispatch(IgemmParams& p, int prec, long long b_lo_off, cudaStream_t s
       if (rc) return rc;
       rc = make_dy_tmap(&tm_lo, p.w + b_lo_off, p.red_len, p.M);
       if (rc) return rc;
+      // CTA-pair kernel (256 output channels per pair, each CTA gathers half of the im2col tile) when there are at
+      // least two channel tiles; CAVP_WGRAD_PAIR=0/1 forces it off/on
+      static const char* pair_env = getenv("CAVP_WGRAD_PAIR");
+      const bool pair = bn == 128 && p.M > BM && (pair_env ? pair_env[0] != '0' : true);
+      if (pair) return prec == 2 ? launch_wgrad2<2>(p, tm_hi, tm_lo, st) : launch_wgrad2<1>(p, tm_hi, tm_lo, st);
       if (prec == 2)
         return bn == 128 ? launch_igemm<128, 2, MODE, true>(p, tm_hi, tm_lo, st)
                          : launch_igemm<64, 2, MODE, true>(p, tm_hi, tm_lo, st);

@@ -312,7 +312,7 @@ class Graph:
         forced = os.environ.get("CAVP_WGRAD_TMA")
         if forced is not None:
             return forced != "0"
-        return K >= 1024 and cout >= 32
+        return cout >= 32 and (K >= 1024 or (K >= 512 and cout >= 512))
 
     @staticmethod
     def colreduce_blocks(M, C):
