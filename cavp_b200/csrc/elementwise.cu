@@ -168,7 +168,7 @@ __global__ void bn_apply_kernel(const float* __restrict__ y, int ldy, const floa
     const float4 v = *reinterpret_cast<const float4*>(y + r * ldy + c4 * 4);
     const float4 sc = *reinterpret_cast<const float4*>(scale + c4 * 4);
     const float4 sh = *reinterpret_cast<const float4*>(shift + c4 * 4);
-    float4 o = make_float4(v.x * sc.x + sh.x, v.y * sc.y + sh.y, v.z * sc.z + sh.z, v.w * sc.w + sh.w);
+    float4 o = make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w));
     if (res) {
       const float4 rr = *reinterpret_cast<const float4*>(res + r * ldr + c4 * 4);
       o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
@@ -184,7 +184,8 @@ __global__ void bn_apply_kernel(const float* __restrict__ y, int ldy, const floa
 __global__ void colreduce_kernel(const float* __restrict__ dz, int lddz, const float* __restrict__ z, int ldz,
                                  const float* __restrict__ y, int ldy, const float* __restrict__ mean,
                                  const float* __restrict__ invstd, long long rows, int C4, int act, float slope,
-                                 float* __restrict__ gout, int ldg, float* __restrict__ partials, int ldp) {
+                                 float* __restrict__ gout, int ldg, float* __restrict__ partials, int ldp,
+                                 const float* __restrict__ zscale, const float* __restrict__ zshift) {
   __shared__ float4 sh[2][4][64];
   const int cl = threadIdx.x & 63, rl = threadIdx.x >> 6;
   const int c4 = blockIdx.x * 64 + cl;
@@ -193,22 +194,34 @@ __global__ void colreduce_kernel(const float* __restrict__ dz, int lddz, const f
   const long long rend = rbeg + rows_per < rows ? rbeg + rows_per : rows;
   float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
   if (c4 < C4) {
-    float4 mu = s1, is = s1;
+    float4 mu = s1, is = s1, zs = s1, zb = s1;
     if (y) {
       mu = *reinterpret_cast<const float4*>(mean + c4 * 4);
       is = *reinterpret_cast<const float4*>(invstd + c4 * 4);
     }
+    // zscale given (and z == NULL): the activation input is recomputed as fma(y, scale, shift) - the expression of
+    // bn_apply_kernel - instead of reading the activation output z back (one tensor read less)
+    const bool remask = !z && zscale && y && act != 0;
+    if (remask) {
+      zs = *reinterpret_cast<const float4*>(zscale + c4 * 4);
+      zb = *reinterpret_cast<const float4*>(zshift + c4 * 4);
+    }
+#pragma unroll 2
     for (long long r = rbeg + rl; r < rend; r += 4) {
       float4 g = *reinterpret_cast<const float4*>(dz + r * lddz + c4 * 4);
+      float4 yy = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (y) yy = *reinterpret_cast<const float4*>(y + r * ldy + c4 * 4);
       if (z) {
         const float4 zz = *reinterpret_cast<const float4*>(z + r * ldz + c4 * 4);
         g.x *= act_bwd_from_out(zz.x, act, slope); g.y *= act_bwd_from_out(zz.y, act, slope);
         g.z *= act_bwd_from_out(zz.z, act, slope); g.w *= act_bwd_from_out(zz.w, act, slope);
+      } else if (remask) {
+        g.x *= act_bwd_from_out(fmaf(yy.x, zs.x, zb.x), act, slope); g.y *= act_bwd_from_out(fmaf(yy.y, zs.y, zb.y), act, slope);
+        g.z *= act_bwd_from_out(fmaf(yy.z, zs.z, zb.z), act, slope); g.w *= act_bwd_from_out(fmaf(yy.w, zs.w, zb.w), act, slope);
       }
       if (gout) *reinterpret_cast<float4*>(gout + r * ldg + c4 * 4) = g;
       s1.x += g.x; s1.y += g.y; s1.z += g.z; s1.w += g.w;
       if (y) {
-        const float4 yy = *reinterpret_cast<const float4*>(y + r * ldy + c4 * 4);
         s2.x += g.x * (yy.x - mu.x) * is.x; s2.y += g.y * (yy.y - mu.y) * is.y;
         s2.z += g.z * (yy.z - mu.z) * is.z; s2.w += g.w * (yy.w - mu.w) * is.w;
       }
@@ -259,21 +272,27 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dz, int lddz, cons
                                     const float* __restrict__ invstd, const float* __restrict__ gamma,
                                     const float* __restrict__ sums, float inv_count, long long rows, int C4, int act,
                                     float slope, float* __restrict__ dy, int lddy, float* __restrict__ dres,
-                                    int lddres) {
+                                    int lddres, const float* __restrict__ zscale, const float* __restrict__ zshift) {
   const long long total = rows * C4;
   const int C = C4 * 4;
+  const bool remask = !z && zscale && act != 0;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long r = i / C4;
     const int c = static_cast<int>(i - r * C4) * 4;
     float4 g = *reinterpret_cast<const float4*>(dz + r * lddz + c);
+    const float4 yy = *reinterpret_cast<const float4*>(y + r * ldy + c);
     if (z) {
       const float4 zz = *reinterpret_cast<const float4*>(z + r * ldz + c);
       g.x *= act_bwd_from_out(zz.x, act, slope); g.y *= act_bwd_from_out(zz.y, act, slope);
       g.z *= act_bwd_from_out(zz.z, act, slope); g.w *= act_bwd_from_out(zz.w, act, slope);
+    } else if (remask) {
+      const float4 zs = *reinterpret_cast<const float4*>(zscale + c);
+      const float4 zb = *reinterpret_cast<const float4*>(zshift + c);
+      g.x *= act_bwd_from_out(fmaf(yy.x, zs.x, zb.x), act, slope); g.y *= act_bwd_from_out(fmaf(yy.y, zs.y, zb.y), act, slope);
+      g.z *= act_bwd_from_out(fmaf(yy.z, zs.z, zb.z), act, slope); g.w *= act_bwd_from_out(fmaf(yy.w, zs.w, zb.w), act, slope);
     }
     if (dres) *reinterpret_cast<float4*>(dres + r * lddres + c) = g;
-    const float4 yy = *reinterpret_cast<const float4*>(y + r * ldy + c);
     const float4 mu = *reinterpret_cast<const float4*>(mean + c);
     const float4 is = *reinterpret_cast<const float4*>(invstd + c);
     const float4 ga = gamma ? *reinterpret_cast<const float4*>(gamma + c) : make_float4(1.f, 1.f, 1.f, 1.f);
@@ -553,12 +572,13 @@ extern "C" int cavp_bn_apply(const float* y, int ldy, const float* scale, const 
 }
 extern "C" int cavp_colreduce(const float* dz, int lddz, const float* z, int ldz, const float* y, int ldy,
                               const float* mean, const float* invstd, long long rows, int C, int act, float slope,
-                              float* gout, int ldg, float* partials, int ldp, int nblk, void* stream) {
+                              float* gout, int ldg, float* partials, int ldp, int nblk, const float* zscale,
+                              const float* zshift, void* stream) {
   if ((C & 3) || (lddz & 3) || (z && (ldz & 3)) || (y && (ldy & 3)) || (gout && (ldg & 3)) || (ldp & 3))
     return CAVP_ERR_ALIGN;
   dim3 grid((C / 4 + 63) / 64, nblk);
   colreduce_kernel<<<grid, 256, 0, ST(stream)>>>(dz, lddz, z, ldz, y, ldy, mean, invstd, rows, C / 4, act, slope, gout,
-                                                 ldg, partials, ldp);
+                                                 ldg, partials, ldp, zscale, zshift);
   CAVP_LAUNCH_CHECK();
 }
 extern "C" int cavp_partials_sum(const float* partials, int nparts, int ldp, int C, int nk, float* out, void* stream) {
@@ -568,10 +588,11 @@ extern "C" int cavp_partials_sum(const float* partials, int nparts, int ldp, int
 extern "C" int cavp_bn_bwd_apply(const float* dz, int lddz, const float* z, int ldz, const float* y, int ldy,
                                  const float* mean, const float* invstd, const float* gamma, const float* sums,
                                  float inv_count, long long rows, int C, int act, float slope, float* dy, int lddy,
-                                 float* dres, int lddres, void* stream) {
+                                 float* dres, int lddres, const float* zscale, const float* zshift, void* stream) {
   if ((C & 3) || (lddz & 3) || (ldy & 3) || (lddy & 3)) return CAVP_ERR_ALIGN;
   bn_bwd_apply_kernel<<<grid_for(rows * (C / 4), 256), 256, 0, ST(stream)>>>(
-      dz, lddz, z, ldz, y, ldy, mean, invstd, gamma, sums, inv_count, rows, C / 4, act, slope, dy, lddy, dres, lddres);
+      dz, lddz, z, ldz, y, ldy, mean, invstd, gamma, sums, inv_count, rows, C / 4, act, slope, dy, lddy, dres, lddres,
+      zscale, zshift);
   CAVP_LAUNCH_CHECK();
 }
 extern "C" int cavp_maxpool_fwd(const float* x, int ldx, float* y, int ldy, int* idx, int n, int h, int w, int c, int k,

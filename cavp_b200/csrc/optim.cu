@@ -85,6 +85,48 @@ opt_multi_kernel(const OptTensor* __restrict__ table, const int2* __restrict__ w
   }
 }
 
+// ---- TF32 hi | lo split of every weight operand of the model in ONE launch (the per-weight cavp_split_tf32 launches
+// were launch-bound: ~230 kernels of a few microseconds per step).  Table rows {src, hi, lo, n}; same work list format.
+struct SplitTensor {
+  const float* src;
+  float* hi;
+  float* lo;
+  long long n;
+};
+static_assert(sizeof(SplitTensor) == 32, "table row layout");
+
+__device__ __forceinline__ float tf32_rn_(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+}
+
+__global__ void __launch_bounds__(OPT_THREADS)
+split_multi_kernel(const SplitTensor* __restrict__ table, const int2* __restrict__ work, int nwork) {
+  for (int wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
+    const int2 w = work[wi];
+    const SplitTensor t = table[w.x];
+    const long long off = static_cast<long long>(w.y) * OPT_CHUNK;
+    const int n = static_cast<int>(t.n - off < OPT_CHUNK ? t.n - off : OPT_CHUNK);
+    const float* src = t.src + off;
+    float* hi = t.hi + off;
+    float* lo = t.lo + off;
+    const uintptr_t al = reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo);
+    const int n4 = (al & 15) == 0 ? (n >> 2) : 0;
+    for (int i = threadIdx.x; i < n4; i += OPT_THREADS) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+      const float h0 = tf32_rn_(v.x), h1 = tf32_rn_(v.y), h2 = tf32_rn_(v.z), h3 = tf32_rn_(v.w);
+      reinterpret_cast<float4*>(hi)[i] = make_float4(h0, h1, h2, h3);
+      reinterpret_cast<float4*>(lo)[i] =
+          make_float4(tf32_rn_(v.x - h0), tf32_rn_(v.y - h1), tf32_rn_(v.z - h2), tf32_rn_(v.w - h3));
+    }
+    for (int i = n4 * 4 + threadIdx.x; i < n; i += OPT_THREADS) {
+      const float v = src[i];
+      const float h = tf32_rn_(v);
+      hi[i] = h;
+      lo[i] = tf32_rn_(v - h);
+    }
+  }
+}
+
 static int opt_grid(int nwork) {
   const int cap = NUM_SMS * 8;
   return nwork < cap ? (nwork < 1 ? 1 : nwork) : cap;
@@ -117,5 +159,14 @@ extern "C" int cavp_adam_multi(const void* table, const int* work, int nwork, do
             static_cast<float>(1.0 / sqrt(bias_correction2))};
   opt_multi_kernel<AdamOp, true><<<opt_grid(nwork), OPT_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const OptTensor*>(table), reinterpret_cast<const int2*>(work), nwork, op);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int cavp_split_tf32_multi(const void* table, const int* work, int nwork, void* stream) {
+  if (!table || !work) return CAVP_ERR_NULL;
+  if (nwork <= 0) return 0;
+  if ((reinterpret_cast<uintptr_t>(table) & 7) || (reinterpret_cast<uintptr_t>(work) & 7)) return CAVP_ERR_ALIGN;
+  split_multi_kernel<<<opt_grid(nwork), OPT_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const SplitTensor*>(table), reinterpret_cast<const int2*>(work), nwork);
   return static_cast<int>(cudaGetLastError());
 }

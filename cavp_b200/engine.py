@@ -113,8 +113,15 @@ class WeightRef:
     def operand(self):
         """(tensor, lo offset in elements) for cavp_igemm's B operand."""
         if self._split is None:
+            cache = self.g.wcache
+            if cache is not None and self.kind in ("linear", "cl") and self.cout_eff == self.cout:
+                hit = cache.operand(self.param)
+                if hit is not None:
+                    self._split, self._lo_off = hit
+                    return self._split, self._lo_off
             self._split = self._presplit(self.wk)
-        return self._split, self.wk.numel()
+            self._lo_off = self.wk.numel()
+        return self._split, self._lo_off
 
     def operand_t(self):
         if self._wt_split is None:
@@ -146,6 +153,54 @@ class WeightRef:
         g.add_param_grad(p, grad)
 
 
+class WeightSplitCache:
+    """Persistent [hi | lo] TF32 splits of every K-major weight operand of a model (channels_last conv weights with
+    Cin % 4 == 0 and Linear weights), refreshed by ONE kernel launch per step (cavp_split_tf32_multi).  The buffers and
+    the device table are built once; they are rebuilt if a parameter's storage moves."""
+
+    def __init__(self, params, device):
+        self.params = list(params)
+        self.device = device
+        self.ptrs = [p.data_ptr() for p in self.params]
+        total = sum(p.numel() for p in self.params)
+        self.buf = torch.empty(2, total, device=device, dtype=torch.float32)
+        self.views, rows, sizes, off = {}, [], [], 0
+        for p in self.params:
+            n = p.numel()
+            hi, lo = self.buf[0, off:off + n], self.buf[1, off:off + n]
+            self.views[id(p)] = (hi, lo)
+            rows.append((p.data_ptr(), hi.data_ptr(), lo.data_ptr(), n))
+            sizes.append(n)
+            off += n
+        chunk = _C.query("cavp_opt_chunk_elems")
+        work = [(i, c) for i, n in enumerate(sizes) for c in range((n + chunk - 1) // chunk)]
+        self.table = torch.tensor(rows, dtype=torch.int64).to(device)
+        self.work = torch.tensor(work, dtype=torch.int32).reshape(-1, 2).to(device)
+        self.lo_off = total  # lo = hi + total elements for every weight
+
+    @staticmethod
+    def eligible(model):
+        out = []
+        for mod in model.modules():
+            w = getattr(mod, "weight", None)
+            if isinstance(mod, torch.nn.Linear) and w is not None and w.is_contiguous():
+                out.append(w)
+            elif isinstance(mod, torch.nn.Conv2d) and w.shape[1] % 4 == 0 and w.permute(0, 2, 3, 1).is_contiguous():
+                out.append(w)
+        return out
+
+    def valid(self):
+        return all(p.data_ptr() == q for p, q in zip(self.params, self.ptrs))
+
+    def operand(self, param):
+        """(hi tensor viewed [cout, K], lo offset in elements) or None"""
+        v = self.views.get(id(param))
+        if v is None:
+            return None
+        cout = param.shape[0]
+        return v[0].view(cout, -1), self.lo_off
+
+
 class Graph:
     def __init__(self, device, prec=2, train=True, sync_bn_group=None):
         self.device = device
@@ -161,6 +216,19 @@ class Graph:
         _C.lib()
         self._fns = _C._fns
         self._work = (0.0, 0.0, "")
+        self.wcache = None
+
+    def use_weight_cache(self, model):
+        """Refresh (one launch) the persistent TF32 splits of the model's weight operands for this step."""
+        cache = model.__dict__.get("_cavp_wsplit")
+        if cache is None or cache.device != self.device or not cache.valid():
+            params = WeightSplitCache.eligible(model)
+            if not params:
+                return
+            cache = WeightSplitCache(params, self.device)
+            model.__dict__["_cavp_wsplit"] = cache
+        self.call("cavp_split_tf32_multi", cache.table.data_ptr(), cache.work.data_ptr(), cache.work.shape[0])
+        self.wcache = cache
 
     # ------------------------------------------------------------------ small helpers
     def call(self, name, *args):
@@ -325,7 +393,7 @@ class Graph:
         self.zero_act(window)
         nblk = min(nparts, self.colreduce_blocks(y.rows, y.c))
         self.call("cavp_colreduce", y.ptr, y.ld, 0, 0, y.ptr, y.ld, self.const_vec(y.c, 0).data_ptr(),
-                  self.const_vec(y.c, 1).data_ptr(), y.rows, y.c, ACT_NONE, 0.0, 0, 0, stats_ptr, ldstat, nblk)
+                  self.const_vec(y.c, 1).data_ptr(), y.rows, y.c, ACT_NONE, 0.0, 0, 0, stats_ptr, ldstat, nblk, 0, 0)
 
     # ------------------------------------------------------------------ conv / linear
     def conv(self, x, w, *, stride=1, pad=0, dil=1, bias=None, act=ACT_NONE, want_stats=False, out=None, res=None,
@@ -422,7 +490,7 @@ class Graph:
                         self.call("cavp_colreduce", g.ptr, g.ld, 0 if zin is None else zin.ptr,
                                   0 if zin is None else zin.ld, 0, 0, 0, 0, M, co, act if zin is not None else ACT_NONE,
                                   LEAKY_SLOPE, 0 if gout is None else gout.ptr, 0 if gout is None else gout.ld,
-                                  partials.data_ptr(), co, nblk)
+                                  partials.data_ptr(), co, nblk, 0, 0)
                         if gout is not None:
                             g = gout
                         if bias is not None and bias.requires_grad:
@@ -500,10 +568,14 @@ class Graph:
             M = y.rows
             nblk = self.colreduce_blocks(M, C)
             partials = self.empty(nblk, 2, C)
-            zin = z if act != ACT_NONE else None
+            # without a residual the activation input is fma(y, scale, shift): the kernels recompute the ReLU mask from y
+            # (which they read anyway) instead of reading z back; with a residual z is the only record of the sign
+            remask = act != ACT_NONE and res is None
+            zin = z if (act != ACT_NONE and not remask) else None
+            zs, zb = (coeffs[2].data_ptr(), coeffs[3].data_ptr()) if remask else (0, 0)
             self.call("cavp_colreduce", dz.ptr, dz.ld, 0 if zin is None else zin.ptr, 0 if zin is None else zin.ld,
                       y.ptr, y.ld, coeffs[0].data_ptr(), coeffs[1].data_ptr(), M, C, act, LEAKY_SLOPE, 0, 0,
-                      partials.data_ptr(), C, nblk)
+                      partials.data_ptr(), C, nblk, zs, zb)
             sums = self.empty(2, C)
             self.call("cavp_partials_sum", partials.data_ptr(), nblk, C, C, 2, sums.data_ptr())
             local = sums
@@ -524,7 +596,7 @@ class Graph:
             self.call("cavp_bn_bwd_apply", dz.ptr, dz.ld, 0 if zin is None else zin.ptr, 0 if zin is None else zin.ld,
                       y.ptr, y.ld, coeffs[0].data_ptr(), coeffs[1].data_ptr(), bn.weight.data_ptr(), sums.data_ptr(),
                       1.0 / count, M, C, act, LEAKY_SLOPE, dy.ptr, dy.ld, 0 if tgt is None else tgt.ptr,
-                      0 if tgt is None else tgt.ld)
+                      0 if tgt is None else tgt.ld, zs, zb)
             if tmp is not None:
                 self.add_act(dres, tmp)
         self.tape.append(bwd)

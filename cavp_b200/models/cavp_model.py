@@ -548,6 +548,7 @@ class CAVP(nn.Module):
             raise RuntimeError("cavp_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
         with torch.no_grad():
             g = Graph(image.device, prec=self.prec, train=False)
+            g.use_weight_cache(self)
             logits, fusion, proj, fea_a, attn = self.build_graph(g, image, audio)
             pred = g.upsample_to_nchw(logits, self.num_classes, image.shape[-2], image.shape[-1])
             self.last_launches = g.launches
@@ -564,6 +565,7 @@ class CAVP(nn.Module):
         nc = self.num_classes
         with torch.no_grad():
             g = Graph(image.device, prec=self.prec, train=False)
+            g.use_weight_cache(self)
             logits, fusion, proj, fea_a, attn = self.build_graph(g, image, audio)
             H, W = image.shape[-2:]
             if conf is None:
@@ -598,6 +600,7 @@ class _CAVPFunction(torch.autograd.Function):
         if not image.is_cuda:
             raise RuntimeError("cavp_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
         g = Graph(image.device, prec=model.prec, train=model.training, sync_bn_group=model._sync_group())
+        g.use_weight_cache(model)
         if not model.training:
             raise RuntimeError("forward_train called in eval mode; use eval_mode=True (reference: forward_inference)")
         logits, fusion, proj, fea_a, attn = model.build_graph(g, image, audio, shuffle_idx=shuffle_idx,

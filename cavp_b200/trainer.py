@@ -47,6 +47,7 @@ def train_step(model, image, audio, pix_label, shuffle_pix_label, *, temperature
     nc = m.num_classes
     g = Graph(dev, prec=m.prec, train=True, sync_bn_group=m._sync_group())
     g.profile = profile
+    g.use_weight_cache(m)
     if labels_dev is None:
         labels_dev = pix_label.to(dev, torch.int64, non_blocking=True)
     labels_dev = labels_dev.contiguous()

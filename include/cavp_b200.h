@@ -46,6 +46,9 @@ int cavp_igemm(const float* x, const float* w, float* y, float* y_pre, const flo
  * b_lo_off = (lo - hi) > 0 to cavp_igemm makes the kernel fetch the weight operand with TMA (cp.async.bulk.tensor, 128B
  * swizzle) instead of through the producer warps; b_lo_off = 0 keeps the in-kernel split (operand = activations). */
 int cavp_split_tf32(const float* w, float* hi, float* lo, long long n, void* stream);
+/* the same split for every weight operand of a model in ONE launch: table = device array of 32-byte rows {const float*
+ * src; float* hi; float* lo; long long n}, work = (row, chunk) int pairs with chunk = cavp_opt_chunk_elems() elements */
+int cavp_split_tf32_multi(const void* table, const int* work, int nwork, void* stream);
 /* cavp_igemm_wgrad: dw[cout][r*s*c] (+)= dy[P][cout]^T * im2col(x)[P][r*s*c]   (weight gradient; P = nimg*ho*wo).
  *   splits > 1 accumulates into a PRE-ZEROED dw. */
 int cavp_igemm_wgrad(const float* dy, const float* x, float* dw, int nimg, int hs, int ws, int c, int ldx, int ho,
@@ -88,16 +91,19 @@ int cavp_bn_eval_coeffs(const float* gamma, const float* beta, const float* rm, 
 /* out = act(y*scale + shift (+ res))   (BN apply + ReLU / LeakyReLU(0.01) + Bottleneck residual, resnet.py:86-96) */
 int cavp_bn_apply(const float* y, int ldy, const float* scale, const float* shift, const float* res, int ldr, float* out,
                   int ldo, long long rows, int C, int act, float slope, void* stream);
-/* column partial sums of g = dz*act'(z) and g*xhat (xhat from y, mean, invstd; y may be NULL -> plain column sums =
+/* zscale / zshift (colreduce, bn_bwd_apply): with z == NULL and an activation, act'(.) is taken from the recomputed
+ * activation input fma(y, zscale, zshift) - the BN-apply expression - instead of reading the output z back.
+ * column partial sums of g = dz*act'(z) and g*xhat (xhat from y, mean, invstd; y may be NULL -> plain column sums =
  * bias gradient); optionally writes g.  partials: [nblk][2][ldp]. */
 int cavp_colreduce(const float* dz, int lddz, const float* z, int ldz, const float* y, int ldy, const float* mean,
                    const float* invstd, long long rows, int C, int act, float slope, float* gout, int ldg,
-                   float* partials, int ldp, int nblk, void* stream);
+                   float* partials, int ldp, int nblk, const float* zscale, const float* zshift, void* stream);
 int cavp_partials_sum(const float* partials, int nparts, int ldp, int C, int nk, float* out, void* stream);
 /* dy = gamma*invstd*(g - sum_g/count - xhat*sum_gxhat/count); dres = g (gradient of the residual input) */
 int cavp_bn_bwd_apply(const float* dz, int lddz, const float* z, int ldz, const float* y, int ldy, const float* mean,
                       const float* invstd, const float* gamma, const float* sums, float inv_count, long long rows, int C,
-                      int act, float slope, float* dy, int lddy, float* dres, int lddres, void* stream);
+                      int act, float slope, float* dy, int lddy, float* dres, int lddres, const float* zscale,
+                      const float* zshift, void* stream);
 
 /* ---- pooling (F.max_pool2d resnet.py:189 / vgg.py:30; ASPP global pooling encoder_decoder.py:158-164;
  *      AdaptiveMaxPool2d audio_network.py:24) ------------------------------------------------------------------- */
