@@ -32,8 +32,11 @@ __global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, float* __rest
   }
 }
 // dst[b][cidx][r] = src[b][r][cidx] with leading dimensions; 32x32 tiles through shared memory
-__global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols,
-                                 long long src_ld, long long dst_ld, long long src_bs, long long dst_bs) {
+// dst[b][j][i] = src[b][i][j]; with `lo` the transposed matrix is written as its TF32 split (hi -> dst, lo -> lo): the
+// data-gradient GEMM's weight operand in one pass instead of transpose + split
+__global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, float* __restrict__ lo,
+                                 int rows, int cols, long long src_ld, long long dst_ld, long long src_bs,
+                                 long long dst_bs) {
   __shared__ float tile[32][33];
   const float* s = src + blockIdx.z * src_bs;
   float* d = dst + blockIdx.z * dst_bs;
@@ -45,7 +48,16 @@ __global__ void transpose_kernel(const float* __restrict__ src, float* __restric
   __syncthreads();
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
     const int cc = c0 + j, r = r0 + threadIdx.x;
-    if (cc < cols && r < rows) d[cc * dst_ld + r] = tile[threadIdx.x][j];
+    if (cc < cols && r < rows) {
+      const float v = tile[threadIdx.x][j];
+      if (lo) {
+        const float h = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
+        d[cc * dst_ld + r] = h;
+        lo[blockIdx.z * dst_bs + cc * dst_ld + r] = __uint_as_float((__float_as_uint(v - h) + 0x1000u) & 0xFFFFE000u);
+      } else {
+        d[cc * dst_ld + r] = v;
+      }
+    }
   }
 }
 __global__ void add_inplace_kernel(float* __restrict__ dst, const float* __restrict__ src, long long n4, float alpha) {
@@ -536,7 +548,14 @@ extern "C" int cavp_nhwc_to_nchw(const float* src, float* dst, int n, int c, int
 extern "C" int cavp_transpose(const float* src, float* dst, int rows, int cols, long long src_ld, long long dst_ld,
                               int batch, long long src_bs, long long dst_bs, void* stream) {
   dim3 grid((cols + 31) / 32, (rows + 31) / 32, batch), block(32, 8);
-  transpose_kernel<<<grid, block, 0, ST(stream)>>>(src, dst, rows, cols, src_ld, dst_ld, src_bs, dst_bs);
+  transpose_kernel<<<grid, block, 0, ST(stream)>>>(src, dst, nullptr, rows, cols, src_ld, dst_ld, src_bs, dst_bs);
+  CAVP_LAUNCH_CHECK();
+}
+extern "C" int cavp_transpose_split(const float* src, float* hi, float* lo, int rows, int cols, long long src_ld,
+                                    long long dst_ld, int batch, long long src_bs, long long dst_bs, void* stream) {
+  if (!src || !hi || !lo) return CAVP_ERR_NULL;
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32, batch), block(32, 8);
+  transpose_kernel<<<grid, block, 0, ST(stream)>>>(src, hi, lo, rows, cols, src_ld, dst_ld, src_bs, dst_bs);
   CAVP_LAUNCH_CHECK();
 }
 extern "C" int cavp_add_inplace(float* dst, const float* src, long long n, float alpha, void* stream) {

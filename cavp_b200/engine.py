@@ -124,9 +124,14 @@ class WeightRef:
         return self._split, self._lo_off
 
     def operand_t(self):
+        """[hi | lo] split of the transposed operand [Cin][taps][Cout_eff] for the data-gradient GEMM (one kernel)."""
         if self._wt_split is None:
-            self._wt_split = self._presplit(self.transposed())
-        return self._wt_split, self._wt.numel()
+            taps = self.r * self.s
+            sp = self.g.empty(2, self.cin, taps * self.cout_eff)
+            self.g.call("cavp_transpose_split", self.wk.data_ptr(), sp[0].data_ptr(), sp[1].data_ptr(), self.cout_eff,
+                        self.cin, taps * self.cin, taps * self.cout_eff, taps, self.cin, self.cout_eff)
+            self._wt_split = sp
+        return self._wt_split, self._wt_split[0].numel()
 
     def transposed(self):
         """[Cin][taps][Cout_eff] for the data-gradient GEMM."""

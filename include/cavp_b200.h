@@ -73,6 +73,9 @@ int cavp_nhwc_to_nchw(const float* src, float* dst, int n, int c, int hw, int ld
 /* dst[b][j][i] = src[b][i][j] (weight transposes for dgrad / the InfoNCE gradient GEMM) */
 int cavp_transpose(const float* src, float* dst, int rows, int cols, long long src_ld, long long dst_ld, int batch,
                    long long src_bs, long long dst_bs, void* stream);
+/* the same transpose writing the TF32 split of the result (hi, lo): the dgrad weight operand in one pass */
+int cavp_transpose_split(const float* src, float* hi, float* lo, int rows, int cols, long long src_ld, long long dst_ld,
+                         int batch, long long src_bs, long long dst_bs, void* stream);
 int cavp_add_inplace(float* dst, const float* src, long long n, float alpha, void* stream);
 /* dst[i] = src[idx[i]] (fea_a[shuffle_idx], models/cavp_model.py:171) or, accumulate_scatter=1, dst[idx[i]] += src[i] */
 int cavp_gather_rows(const float* src, const long long* idx, float* dst, int nrows, int c, int accumulate_scatter,
