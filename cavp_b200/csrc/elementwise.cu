@@ -94,7 +94,49 @@ __global__ void gather_rows_kernel(const float* __restrict__ src, const long lon
 // ------------------------------------------------------------------------------------------------ BatchNorm
 // Reduce the per-(m_tile, quarter) partial sums written by the igemm epilogue (fp64 accumulate) and finish the batch
 // statistics.  block = (32 channels, 32 part-lanes): reads are coalesced across channels.
-__global__ void bn_finalize_kernel(const float* __restrict__ partials, int nparts, int ldstat, int C, double count,
+// stage 1 of the two-stage finalize: block (x = 32 channels, y = slice s of the partial rows) -> one fp64 row
+// ws[s][2][C].  A single block per 32 channels reading 12 K partial rows is bound by one SM's load bandwidth (~20 us
+// per layer at 112x112); sixteen slices per channel group spread the same bytes over 16x more SMs.
+__global__ void bn_partial_reduce_kernel(const float* __restrict__ partials, int nparts, int ldstat, int C,
+                                         double* __restrict__ ws) {
+  __shared__ double sh1[32][33], sh2[32][33];
+  const int ch = blockIdx.x * 32 + threadIdx.x;
+  const int S = gridDim.y, sl = blockIdx.y;
+  const int per = (nparts + S - 1) / S;
+  const int beg = sl * per, end = min(nparts, beg + per);
+  double t1[4] = {0.0, 0.0, 0.0, 0.0}, t2[4] = {0.0, 0.0, 0.0, 0.0};
+  if (ch < C) {
+    int i = beg + threadIdx.y;
+    for (; i + 96 < end; i += 128) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float* pp = partials + static_cast<size_t>(i + 32 * u) * 2 * ldstat;
+        t1[u] += pp[ch];
+        t2[u] += pp[ldstat + ch];
+      }
+    }
+    for (; i < end; i += 32) {
+      const float* pp = partials + static_cast<size_t>(i) * 2 * ldstat;
+      t1[0] += pp[ch];
+      t2[0] += pp[ldstat + ch];
+    }
+  }
+  sh1[threadIdx.y][threadIdx.x] = (t1[0] + t1[1]) + (t1[2] + t1[3]);
+  sh2[threadIdx.y][threadIdx.x] = (t2[0] + t2[1]) + (t2[2] + t2[3]);
+  __syncthreads();
+  if (threadIdx.y == 0 && ch < C) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int j = 0; j < 32; ++j) {
+      s1 += sh1[j][threadIdx.x];
+      s2 += sh2[j][threadIdx.x];
+    }
+    ws[(static_cast<size_t>(sl) * 2 + 0) * C + ch] = s1;
+    ws[(static_cast<size_t>(sl) * 2 + 1) * C + ch] = s2;
+  }
+}
+
+template <typename PT>
+__global__ void bn_finalize_kernel(const PT* __restrict__ partials, int nparts, int ldstat, int C, double count,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
                                    float eps, float* __restrict__ mean_out, float* __restrict__ invstd_out,
@@ -111,13 +153,13 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partials, int npart
     for (; i + 96 < nparts; i += 128) {
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const float* pp = partials + static_cast<size_t>(i + 32 * u) * 2 * ldstat;
+        const PT* pp = partials + static_cast<size_t>(i + 32 * u) * 2 * ldstat;
         t1[u] += pp[ch];
         t2[u] += pp[ldstat + ch];
       }
     }
     for (; i < nparts; i += 32) {
-      const float* pp = partials + static_cast<size_t>(i) * 2 * ldstat;
+      const PT* pp = partials + static_cast<size_t>(i) * 2 * ldstat;
       t1[0] += pp[ch];
       t2[0] += pp[ldstat + ch];
     }
@@ -572,7 +614,26 @@ extern "C" int cavp_bn_finalize(const float* partials, int nparts, int ldstat, i
                                 const float* beta, float* running_mean, float* running_var, float momentum, float eps,
                                 float* mean_out, float* invstd_out, float* scale_out, float* shift_out, double* sums_io,
                                 int sums_mode, void* stream) {
-  bn_finalize_kernel<<<(C + 31) / 32, dim3(32, 32), 0, ST(stream)>>>(
+  constexpr int S = 16, WS_C = 8192;
+  if (sums_mode != 2 && nparts >= 512 && C <= WS_C) {
+    // two-stage path; the fp64 workspace is per device and reused by every call (launches of one stream are ordered;
+    // the engine issues all BatchNorm work on one stream)
+    static double* ws_dev[64] = {nullptr};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return CAVP_ERR_ARG;
+    if (!ws_dev[dev]) {
+      cudaError_t e = cudaMalloc(&ws_dev[dev], sizeof(double) * S * 2 * WS_C);
+      if (e != cudaSuccess) return static_cast<int>(e);
+    }
+    bn_partial_reduce_kernel<<<dim3((C + 31) / 32, S), dim3(32, 32), 0, ST(stream)>>>(partials, nparts, ldstat, C,
+                                                                                    ws_dev[dev]);
+    bn_finalize_kernel<double><<<(C + 31) / 32, dim3(32, 32), 0, ST(stream)>>>(
+        ws_dev[dev], S, C, C, count, gamma, beta, running_mean, running_var, momentum, eps, mean_out, invstd_out,
+        scale_out, shift_out, sums_io, sums_mode);
+    CAVP_LAUNCH_CHECK();
+  }
+  bn_finalize_kernel<float><<<(C + 31) / 32, dim3(32, 32), 0, ST(stream)>>>(
       partials, nparts, ldstat, C, count, gamma, beta, running_mean, running_var, momentum, eps, mean_out, invstd_out,
       scale_out, shift_out, sums_io, sums_mode);
   CAVP_LAUNCH_CHECK();
