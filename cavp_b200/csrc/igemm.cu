@@ -175,7 +175,8 @@ static int dispatch(IgemmParams& p, int prec, long long b_lo_off, cudaStream_t s
       // CAVP_IGEMM_WS=0/1/2 forces tile / ws / pair.
       const int m_tiles_ = (p.M + BM - 1) / BM;
       const bool heavy_epilogue = (p.res != nullptr && !igemm_inplace_acc(p)) || p.act == ACT_GELU || p.act == ACT_SIGMOID;
-      int sched = prec == 1 ? 1 : (heavy_epilogue ? 0 : ((bn == 128 && m_tiles_ >= 148) ? 2 : 1));
+      const int pair_items = ((m_tiles_ + 1) / 2) * ((p.Ncols + 127) / 128) * p.splits;
+      int sched = prec == 1 ? 1 : (heavy_epilogue ? 0 : ((bn == 128 && m_tiles_ >= 2 && pair_items >= 148) ? 2 : 1));
       if (ws_env) sched = ws_env[0] - '0';
       if (sched == 2 && bn == 128) {  // CTA-pair kernel: each CTA fetches half of the weight rows
         // 160-column tiles when they pad N less than 128-column tiles do (N = 304: 2 x 160 = 320 instead of 3 x 128 = 384)
@@ -296,7 +297,13 @@ extern "C" int cavp_igemm(const float* x, const float* w, float* y, float* y_pre
   p.res_mod = res_mod; p.res_div = res_div; p.ldstat = ldstat; p.act = act; p.slope = slope;
   p.red_len = p.K;
   p.num_kb = (p.K + BK - 1) / BK;
+  // splits < 0: deterministic split-K - y holds |splits| slabs of M*ldy floats, split i stores its raw partial product
+  // in slab i (no atomics, no pre-zeroing); the caller sums the slabs in a fixed order
+  const bool slabs = splits < -1;
+  if (slabs) splits = -splits;
   p.splits = splits < 1 ? 1 : (splits > p.num_kb ? p.num_kb : splits);
+  p.split_slab = (slabs && p.splits > 1) ? static_cast<long long>(p.M) * ldy : 0;
+  if (slabs && p.splits != splits) return CAVP_ERR_ARG;  // the caller sized y for exactly |splits| slabs
   if (p.splits > 1 && (y_pre || scale || shift || res || stats || act != ACT_NONE)) return CAVP_ERR_ARG;
   fill_divs(p);
   if (b_lo_off > 0 && ((b_lo_off & 3) || (reinterpret_cast<uintptr_t>(w) & 15))) return CAVP_ERR_ALIGN;

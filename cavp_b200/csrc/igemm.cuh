@@ -55,6 +55,7 @@ struct IgemmParams {
   int act;
   float slope;
   int n_tiles, num_kb, splits;
+  long long split_slab;  // > 0: deterministic split-K - split i stores its partial product at y + i*split_slab (no atomics)
   FastDiv div_howo, div_wo, div_c, div_s;
 };
 
@@ -168,9 +169,16 @@ __host__ __device__ __forceinline__ bool igemm_inplace_acc(const IgemmParams& p)
 }
 
 template <int HALF>
-__device__ __forceinline__ void igemm_epilogue(const IgemmParams& p, float (&acc)[HALF], int m0, int n0, int m_tile,
-                                               int group, int q, int lane, uint32_t scratch) {
-  if (m0 >= p.M) return;  // a pair kernel's second CTA can own a tile past the last row: nothing to store, no stats rows
+__device__ __forceinline__ void igemm_epilogue(const IgemmParams& pin, float (&acc)[HALF], int m0, int n0, int m_tile,
+                                               int group, int q, int lane, uint32_t scratch, int split = 0) {
+  if (m0 >= pin.M) return;
+  // deterministic split-K: this split owns a private slab of the output and stores its raw partial product there
+  // (plain epilogue, splits = 1 semantics); a fixed-order reduction over the slabs follows on the host's stream
+  IgemmParams p = pin;
+  if (pin.splits > 1 && pin.split_slab > 0) {
+    p.y = pin.y + static_cast<size_t>(split) * pin.split_slab;
+    p.splits = 1;
+  }  // a pair kernel's second CTA can own a tile past the last row: nothing to store, no stats rows
   const int row = m0 + q * 32 + lane;
   const int row0 = m0 + q * 32;
   const bool row_ok = row < p.M;
@@ -662,7 +670,7 @@ igemm_kernel(const IgemmParams p, const __grid_constant__ CUtensorMap tm_b_hi, c
       promote(0);
     }
 
-    igemm_epilogue<HALF>(p, acc, m0, n0, m_tile, group, q, lane, smem_base + static_cast<uint32_t>(warp * 4608));
+    igemm_epilogue<HALF>(p, acc, m0, n0, m_tile, group, q, lane, smem_base + static_cast<uint32_t>(warp * 4608), split);
   } else {
     // ===================================================== MMA issuer (warp 8: converged loop, one elected lane issues)
     {

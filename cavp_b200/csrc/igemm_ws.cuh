@@ -44,7 +44,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 }
 
 struct WsWork {
-  int m_tile, n_tile, kb_begin, nkb;
+  int m_tile, n_tile, kb_begin, nkb, split;
 };
 __device__ __forceinline__ WsWork ws_decode(const IgemmParams& p, int w) {
   // work item = (tile, split); tiles ordered n-fastest so that concurrently running CTAs share their A rows in L2
@@ -54,6 +54,7 @@ __device__ __forceinline__ WsWork ws_decode(const IgemmParams& p, int w) {
   const int tile = w - split * tiles;
   r.n_tile = tile % p.n_tiles;
   r.m_tile = tile / p.n_tiles;
+  r.split = split;
   r.kb_begin = static_cast<int>((static_cast<long long>(p.num_kb) * split) / p.splits);
   const int kb_end = static_cast<int>((static_cast<long long>(p.num_kb) * (split + 1)) / p.splits);
   r.nkb = kb_end - r.kb_begin;
@@ -135,7 +136,7 @@ igemm_ws_kernel(const IgemmParams p, const __grid_constant__ CUtensorMap tm_b_hi
         mbar_arrive(&acce_bar[b]);
       }
       ubase += nunits;
-      igemm_epilogue<BN>(p, acc, wk.m_tile * BM, wk.n_tile * BN, wk.m_tile, 0, q, lane, scratch);
+      igemm_epilogue<BN>(p, acc, wk.m_tile * BM, wk.n_tile * BN, wk.m_tile, 0, q, lane, scratch, wk.split);
     }
   } else if (warp < WS_MMA_WARP) {
     // ================================================================= producers

@@ -40,7 +40,7 @@ struct Ws2Cfg {
 };
 
 struct Ws2Work {
-  int m_pair, n_tile, kb_begin, nkb;
+  int m_pair, n_tile, kb_begin, nkb, split;
 };
 __device__ __forceinline__ Ws2Work ws2_decode(const IgemmParams& p, int w, int m_pairs) {
   Ws2Work r;
@@ -49,6 +49,7 @@ __device__ __forceinline__ Ws2Work ws2_decode(const IgemmParams& p, int w, int m
   const int tile = w - split * tiles;
   r.n_tile = tile % p.n_tiles;
   r.m_pair = tile / p.n_tiles;
+  r.split = split;
   r.kb_begin = static_cast<int>((static_cast<long long>(p.num_kb) * split) / p.splits);
   const int kb_end = static_cast<int>((static_cast<long long>(p.num_kb) * (split + 1)) / p.splits);
   r.nkb = kb_end - r.kb_begin;
@@ -146,7 +147,7 @@ igemm_ws2_kernel(const IgemmParams p, const __grid_constant__ CUtensorMap tm_b_h
         if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&acce_bar[b]), 0));
       }
       ubase += nunits;
-      igemm_epilogue<BN>(p, acc, m_tile * BM, wk.n_tile * BN, m_tile, 0, q, lane, scratch);
+      igemm_epilogue<BN>(p, acc, m_tile * BM, wk.n_tile * BN, m_tile, 0, q, lane, scratch, wk.split);
     }
   } else if (warp < WS_MMA_WARP) {
     // ================================================================= producers
@@ -158,6 +159,74 @@ igemm_ws2_kernel(const IgemmParams p, const __grid_constant__ CUtensorMap tm_b_h
     const int r0 = gtid >> 3;
     const uint32_t swz = static_cast<uint32_t>((c ^ (r0 & 7)) << 4);
     int gbase = 0;  // global k-block counter at the start of the current work item
+    // ---- linear layers (1x1, stride 1, no padding, no split-K, even k-block count): the A row of output row m is row m
+    // of x, so there is no row table to rebuild and the register double buffer keeps running ACROSS tiles - the gather
+    // of the next tile's first k-blocks is in flight while the current tile's last ones are stored.  For K = 304 (10
+    // k-blocks per tile) the per-tile restart (two named barriers, table, exposed first loads) cost ~20 % of the tile.
+    const bool linear = p.R == 1 && p.S == 1 && p.stride == 1 && p.pad == 0 && p.splits == 1 && (p.num_kb & 1) == 0 &&
+                        p.Hs == p.Ho && p.Ws == p.Wo;
+    if (linear) {
+      const int nkb = p.num_kb;
+      struct Pos { int w, it, m0, nb0; };
+      auto decode = [&](int w, int it) {
+        Pos q_{w, it, 0, 0};
+        if (w < total_work) {
+          const Ws2Work wk = ws2_decode(p, w, m_pairs);
+          q_.m0 = (wk.m_pair * 2 + static_cast<int>(rank)) * BM;
+          q_.nb0 = wk.n_tile * BN + static_cast<int>(rank) * Cfg::BH;
+        }
+        return q_;
+      };
+      auto advance = [&](const Pos& a) {
+        if (a.it + 2 < nkb) return Pos{a.w, a.it + 2, a.m0, a.nb0};
+        return decode(a.w + num_pairs, group);
+      };
+      auto load_lin = [&](const Pos& a, float4 (&va)[8]) {
+        const int k = a.it * BK + c * 4;
+        const bool kvalid = k < p.K;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int m = a.m0 + r0 + 16 * i;
+          va[i] = (kvalid && m < p.M) ? ldg_nc_v4(p.x + static_cast<size_t>(m) * p.ldx + k)
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      int G = group;  // this group's k-blocks are every other one of the CTA's global k-block sequence
+      auto body = [&](Pos& cur_pos, float4 (&cur)[8], float4 (&nxt)[8]) {
+        const Pos nxt_pos = advance(cur_pos);
+        if (nxt_pos.w < total_work) load_lin(nxt_pos, nxt);
+        const int s = G % Cfg::STAGES;
+        mbar_wait(&empty_bar[s], (((G / Cfg::STAGES) & 1) ^ 1));
+        const uint32_t a_hi = smem_base + s * Cfg::STAGE_BYTES, a_lo = a_hi + Cfg::A_BYTES;
+        const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[s]), 0);
+        if (gtid < 32) {
+          if (elect_one_sync()) {
+            const uint32_t b_hi = a_hi + Cfg::A_BYTES * PREC;
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * Cfg::B_BYTES * PREC);
+            tma_load_2d_pair(b_hi, &tm_b_hi, full_leader, cur_pos.it * BK, cur_pos.nb0);
+            if (PREC == 2) tma_load_2d_pair(b_hi + Cfg::B_BYTES, &tm_b_lo, full_leader, cur_pos.it * BK, cur_pos.nb0);
+          }
+          __syncwarp();
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t off = static_cast<uint32_t>((r0 + 16 * i) * 128) + swz;
+          store_split_fast<PREC>(a_hi + off, a_lo + off, cur[i]);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(full_leader);
+        G += 2;
+        cur_pos = nxt_pos;
+      };
+      float4 va0[8], va1[8];
+      Pos pos = decode(pair_id, group);
+      if (pos.w < total_work) load_lin(pos, va0);
+      while (pos.w < total_work) {
+        body(pos, va0, va1);
+        if (pos.w < total_work) body(pos, va1, va0);
+      }
+    } else
     for (int w = pair_id; w < total_work; w += num_pairs) {
       const Ws2Work wk = ws2_decode(p, w, m_pairs);
       const int m0 = (wk.m_pair * 2 + static_cast<int>(rank)) * BM;

@@ -435,10 +435,17 @@ class Graph:
         if splits > 1 and (save_pre or res_mod or res_div):
             splits = 1
         if splits > 1:
+            # forward split-K is deterministic: every split stores its partial product in a private slab and the slabs
+            # are summed in a fixed order (red.global.add would make the logits - and near-tie argmax decisions -
+            # depend on the arrival order of the atomics)
             simple = bias_t is None and act == ACT_NONE and res is None
-            raw = y if simple else new_act(x.n, ho, wo, co, self.device)
-            self.zero_act(raw)
-            self._igemm(x, wr.operand(), co, K, raw, geom=geom, splits=splits)
+            raw = y if (simple and y.ld == co and y.off == 0) else new_act(x.n, ho, wo, co, self.device)
+            simple = raw is y
+            nk = (K + 31) // 32
+            splits = min(splits, nk)
+            slabs = new_act(splits * x.n, ho, wo, co, self.device)
+            self._igemm(x, wr.operand(), co, K, Act(slabs.buf[:M], x.n, ho, wo, co), geom=geom, splits=-splits)
+            self.call("cavp_partials_sum", slabs.ptr, splits, M * co, M * co, 1, raw.ptr)
             if not simple:
                 self.call("cavp_bn_apply", raw.ptr, raw.ld, self.const_vec(co, 1).data_ptr(),
                           (bias_t if bias_t is not None else self.const_vec(co, 0)).data_ptr(),
@@ -619,10 +626,13 @@ class Graph:
             wo = (x.w + 2 * pad - dil * (s - 1) - 1) // stride + 1
             y = out if out is not None else new_act(x.n, ho, wo, co, self.device)
             splits = self.fwd_splits(y.rows, co, wr.K)
-            if splits > 1:
+            if splits > 1:  # deterministic split-K (private slabs + fixed-order sum), as in conv()
                 raw = new_act(x.n, ho, wo, co, self.device)
-                self.zero_act(raw)
-                self._igemm(x, wr.operand(), co, wr.K, raw, geom=(ho, wo, r, s, stride, pad, dil), splits=splits)
+                splits = min(splits, (wr.K + 31) // 32)
+                slabs = new_act(splits * x.n, ho, wo, co, self.device)
+                self._igemm(x, wr.operand(), co, wr.K, Act(slabs.buf[:y.rows], x.n, ho, wo, co),
+                            geom=(ho, wo, r, s, stride, pad, dil), splits=-splits)
+                self.call("cavp_partials_sum", slabs.ptr, splits, y.rows * co, y.rows * co, 1, raw.ptr)
                 self.call("cavp_bn_apply", raw.ptr, raw.ld, coeffs[0].data_ptr(), coeffs[1].data_ptr(),
                           0 if res is None else res.ptr, 0 if res is None else res.ld, y.ptr, y.ld, y.rows, co, act,
                           LEAKY_SLOPE)

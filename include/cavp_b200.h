@@ -37,7 +37,9 @@ extern "C" {
  *   epilogue: v = acc*scale[col] + shift[col] + res[(row/res_div)%res_mod][col]; y_pre = v; y = act(v);
  *   stats (optional) receives per-(row-tile, warp) column sums of y and y^2: [ceil(M/128)*4][2][ldstat] - the
  *   BatchNorm batch statistics (train mode) without a second pass over y.
- *   splits > 1 splits K over CTAs and accumulates raw products into a PRE-ZEROED y with red.global (no epilogue). */
+ *   splits > 1 splits K over CTAs and accumulates raw products into a PRE-ZEROED y with red.global (no epilogue).
+ *   splits < -1 is the deterministic form: y holds |splits| slabs of M*ldy floats, split i stores its raw partial
+ *   product in slab i (nothing to pre-zero); the caller reduces the slabs in a fixed order (cavp_partials_sum). */
 int cavp_igemm(const float* x, const float* w, float* y, float* y_pre, const float* scale, const float* shift,
                const float* res, float* stats, int nimg, int hs, int ws, int c, int ldx, int ho, int wo, int r, int s,
                int stride, int pad, int dil, int dgrad, int ncols, int ldw, int ldy, int ldr, int res_mod, int res_div,

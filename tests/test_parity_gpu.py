@@ -233,3 +233,16 @@ def test_forward_audio_path_with_sound_bank_overwrite():
     assert float(model.memory.bank_vault.abs().sum()) > 0  # update_bank queued single-label features
     out_cat.sum().backward()
     assert model.audio_backbone.backbone.fc.weight.grad is not None
+
+
+def test_eval_forward_is_bitwise_deterministic():
+    """Forward split-K stores per-split slabs and sums them in a fixed order (no atomics), BN / LN partials are reduced
+    in a fixed order too: two passes over the same input give identical logits, hence identical argmax masks."""
+    cfg = load_golden("tiny_train")["config"]
+    model = build_model(cfg).eval()
+    batch = batch_for(cfg)
+    img, aud = batch["image"].cuda(), batch["audio"][:cfg["B"]].cuda()
+    with torch.no_grad():
+        p1, f1, _ = model(img, aud, eval_mode=True)
+        p2, f2, _ = model(img, aud, eval_mode=True)
+    assert torch.equal(p1, p2) and torch.equal(f1, f2)
