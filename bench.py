@@ -193,11 +193,30 @@ def run_ours(args):
     launches = [0]
     host_ms = [0.0]
 
+    # e2e input path: pinned host tensors -> device on a copy stream, double-buffered like a DataLoader(pin_memory=True)
+    # prefetcher: the H2D copy of step i+1 overlaps the kernels of step i; every step still copies all of its inputs
+    # inside the timed region (h2d_bytes_per_step) and reads its two losses back (8 bytes, one transfer)
+    copy_stream = torch.cuda.Stream(device=dev)
+    staged = {"bufs": None, "event": None}
+
+    def stage_inputs():
+        with torch.cuda.stream(copy_stream):
+            bufs = [t.to(dev, non_blocking=True) for t in pinned]
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        staged["bufs"], staged["event"] = bufs, ev
+
     def step(resident, profile=None):
         if resident:
             im, au, px = image_d, audio_d, pix_d
         else:
-            im, au, px = (t.to(dev, non_blocking=True) for t in pinned)
+            if staged["bufs"] is None:
+                stage_inputs()
+            torch.cuda.current_stream(dev).wait_event(staged["event"])
+            im, au, px = staged["bufs"]
+            for t in (im, au, px):
+                t.record_stream(torch.cuda.current_stream(dev))
+            stage_inputs()  # next step's copy, overlapping this step's kernels
         opt_v.zero_grad(set_to_none=True)
         opt_a.zero_grad(set_to_none=True)
         res = train_step(model, im, au, pix_h, spl_h, max_views=CFG["max_views"], assign_grads=(flat is None),
@@ -209,7 +228,7 @@ def run_ours(args):
         opt_a.step()
         launches[0] += res.launches + 2  # + the two fused optimiser kernels
         if not resident:
-            return float(res.l_ce), float(res.l_ctr)  # D2H read of the step's result
+            return torch.stack((res.l_ce.reshape(()), res.l_ctr.reshape(()))).tolist()  # D2H read of the step's result
         return res
 
     def timed(resident):

@@ -370,10 +370,12 @@ class Graph:
         bn = 128 if K > 64 else 64
         tiles = ((cout + 127) // 128) * ((K + bn - 1) // bn)
         num_kb = (P + 31) // 32
+        import os
+        overhead = int(os.environ.get("CAVP_WGRAD_OVERHEAD", "12"))
         best, best_cost = 1, None
         for s in range(1, max(1, min(num_kb // 4, 96)) + 1):
             waves = (tiles * s + NUM_SMS - 1) // NUM_SMS
-            cost = waves * ((num_kb + s - 1) // s + 12)
+            cost = waves * ((num_kb + s - 1) // s + overhead)
             if best_cost is None or cost < best_cost:
                 best, best_cost = s, cost
         return best
