@@ -119,3 +119,20 @@ def test_optimizer_work_list_and_cpu_refusal():
         with pytest.raises(RuntimeError):
             opt.step()
     assert [g["lr"] for g in SGD([dict(params=[p], lr=0.5)], lr=0.1, momentum=0.9).param_groups] == [0.5]
+
+
+def test_wgrad_split_heuristic_avoids_wave_spill():
+    """host logic: the weight-gradient split count never lands just past a multiple of 148 CTAs (a 2.03-wave launch
+    costs three waves), and the TMA path is chosen only where enough column tiles re-read dY."""
+    from cavp_b200.engine import Graph, NUM_SMS
+    for P, cout, K in [(200704, 256, 2736), (200704, 1216, 304), (200704, 304, 1216), (25088, 256, 18432),
+                       (25088, 2048, 512), (401408, 128, 576), (200704, 304, 304), (100352, 64, 576), (64, 4096, 12288)]:
+        s = Graph.wgrad_splits(P, cout, K)
+        bn = 128 if K > 64 else 64
+        tiles = ((cout + 127) // 128) * ((K + bn - 1) // bn)
+        ctas = tiles * s
+        waves = (ctas + NUM_SMS - 1) // NUM_SMS
+        assert 1 <= s <= max(1, (P + 31) // 32 // 4)
+        assert ctas > (waves - 1) * NUM_SMS + NUM_SMS // 3 or waves == 1, (P, cout, K, s, ctas)
+    assert Graph.wgrad_via_tma(200704, 256, 2736) and Graph.wgrad_via_tma(25088, 2048, 512)
+    assert not Graph.wgrad_via_tma(200704, 1216, 304) and not Graph.wgrad_via_tma(401408, 16, 4096)
