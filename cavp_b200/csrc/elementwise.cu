@@ -239,10 +239,13 @@ __global__ void colreduce_kernel(const float* __restrict__ dz, int lddz, const f
                                  const float* __restrict__ y, int ldy, const float* __restrict__ mean,
                                  const float* __restrict__ invstd, long long rows, int C4, int act, float slope,
                                  float* __restrict__ gout, int ldg, float* __restrict__ partials, int ldp,
-                                 const float* __restrict__ zscale, const float* __restrict__ zshift) {
-  __shared__ float4 sh[2][4][64];
-  const int cl = threadIdx.x & 63, rl = threadIdx.x >> 6;
-  const int c4 = blockIdx.x * 64 + cl;
+                                 const float* __restrict__ zscale, const float* __restrict__ zshift, int LC) {
+  // LC (16 / 32 / 64) float4 column lanes per block, 256 / LC row lanes: with a fixed 64 x 4 layout the C = 64 layers
+  // (the largest maps of the network) kept 3 of 4 threads idle
+  __shared__ float4 sh[2][256];
+  const int cl = threadIdx.x & (LC - 1), rl = threadIdx.x / LC;
+  const int nrl = 256 / LC;
+  const int c4 = blockIdx.x * LC + cl;
   const long long rows_per = (rows + gridDim.y - 1) / gridDim.y;
   const long long rbeg = blockIdx.y * rows_per;
   const long long rend = rbeg + rows_per < rows ? rbeg + rows_per : rows;
@@ -261,7 +264,7 @@ __global__ void colreduce_kernel(const float* __restrict__ dz, int lddz, const f
       zb = *reinterpret_cast<const float4*>(zshift + c4 * 4);
     }
 #pragma unroll 2
-    for (long long r = rbeg + rl; r < rend; r += 4) {
+    for (long long r = rbeg + rl; r < rend; r += nrl) {
       float4 g = *reinterpret_cast<const float4*>(dz + r * lddz + c4 * 4);
       float4 yy = make_float4(0.f, 0.f, 0.f, 0.f);
       if (y) yy = *reinterpret_cast<const float4*>(y + r * ldy + c4 * 4);
@@ -281,13 +284,12 @@ __global__ void colreduce_kernel(const float* __restrict__ dz, int lddz, const f
       }
     }
   }
-  sh[0][rl][cl] = s1;
-  sh[1][rl][cl] = s2;
+  sh[0][rl * LC + cl] = s1;
+  sh[1][rl * LC + cl] = s2;
   __syncthreads();
   if (rl == 0 && c4 < C4) {
-#pragma unroll
-    for (int k = 1; k < 4; ++k) {
-      const float4 a = sh[0][k][cl], b = sh[1][k][cl];
+    for (int k = 1; k < nrl; ++k) {
+      const float4 a = sh[0][k * LC + cl], b = sh[1][k * LC + cl];
       s1.x += a.x; s1.y += a.y; s1.z += a.z; s1.w += a.w;
       s2.x += b.x; s2.y += b.y; s2.z += b.z; s2.w += b.w;
     }
@@ -656,9 +658,21 @@ extern "C" int cavp_colreduce(const float* dz, int lddz, const float* z, int ldz
                               const float* zshift, void* stream) {
   if ((C & 3) || (lddz & 3) || (z && (ldz & 3)) || (y && (ldy & 3)) || (gout && (ldg & 3)) || (ldp & 3))
     return CAVP_ERR_ALIGN;
-  dim3 grid((C / 4 + 63) / 64, nblk);
-  colreduce_kernel<<<grid, 256, 0, ST(stream)>>>(dz, lddz, z, ldz, y, ldy, mean, invstd, rows, C / 4, act, slope, gout,
-                                                 ldg, partials, ldp, zscale, zshift);
+  const int C4 = C / 4;
+  int LC = 64;  // column lanes per block: the candidate that wastes the fewest lanes on the last block (ties: wider)
+  {
+    int best = -1;
+    for (int cand = 64; cand >= 16; cand >>= 1) {
+      const int util = 1000 * C4 / (((C4 + cand - 1) / cand) * cand);
+      if (util > best) {
+        best = util;
+        LC = cand;
+      }
+    }
+  }
+  dim3 grid((C4 + LC - 1) / LC, nblk);
+  colreduce_kernel<<<grid, 256, 0, ST(stream)>>>(dz, lddz, z, ldz, y, ldy, mean, invstd, rows, C4, act, slope, gout,
+                                                 ldg, partials, ldp, zscale, zshift, LC);
   CAVP_LAUNCH_CHECK();
 }
 extern "C" int cavp_partials_sum(const float* partials, int nparts, int ldp, int C, int nk, float* out, void* stream) {

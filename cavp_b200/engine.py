@@ -391,7 +391,10 @@ class Graph:
 
     @staticmethod
     def colreduce_blocks(M, C):
-        return max(1, min((M + 31) // 32, 4 * NUM_SMS // max(1, (C // 4 + 63) // 64)))
+        c4 = C // 4
+        lc = max((64, 32, 16), key=lambda cand: (1000 * c4 // (((c4 + cand - 1) // cand) * cand), cand))
+        # ^ column lanes per block, the same choice as csrc/elementwise.cu:cavp_colreduce
+        return max(1, min((M + 31) // 32, 4 * NUM_SMS // max(1, (c4 + lc - 1) // lc)))
 
     def stats_from_tensor(self, y, stats):
         """BN statistics partials (sum, sum of squares) of an already materialised tensor (split-K path)."""
