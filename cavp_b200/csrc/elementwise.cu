@@ -211,6 +211,8 @@ __global__ void bn_eval_coeffs_kernel(const float* __restrict__ gamma, const flo
   shift[ch] = b - rm[ch] * g * invstd;
 }
 
+// (flat grid-stride layout: measured faster here than the column-stationary one used by bn_bwd_apply - only two of the
+// four loads are per-channel constants)
 __global__ void bn_apply_kernel(const float* __restrict__ y, int ldy, const float* __restrict__ scale,
                                 const float* __restrict__ shift, const float* __restrict__ res, int ldr,
                                 float* __restrict__ out, int ldo, long long rows, int C4, int act, float slope) {
@@ -323,19 +325,37 @@ __global__ void partials_sum_kernel(const float* __restrict__ partials, int npar
   }
 }
 
-__global__ void bn_bwd_apply_kernel(const float* __restrict__ dz, int lddz, const float* __restrict__ z, int ldz,
-                                    const float* __restrict__ y, int ldy, const float* __restrict__ mean,
-                                    const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                    const float* __restrict__ sums, float inv_count, long long rows, int C4, int act,
-                                    float slope, float* __restrict__ dy, int lddy, float* __restrict__ dres,
-                                    int lddres, const float* __restrict__ zscale, const float* __restrict__ zshift) {
-  const long long total = rows * C4;
+// Column-stationary layout (as colreduce): a thread keeps its four channels' seven coefficient vectors in registers and
+// walks rows, instead of re-loading them for every float4 of a flat grid-stride loop (7 of 10 loads were constants).
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const float* __restrict__ dz, int lddz, const float* __restrict__ z, int ldz,
+                    const float* __restrict__ y, int ldy, const float* __restrict__ mean,
+                    const float* __restrict__ invstd, const float* __restrict__ gamma,
+                    const float* __restrict__ sums, float inv_count, long long rows, int C4, int act,
+                    float slope, float* __restrict__ dy, int lddy, float* __restrict__ dres,
+                    int lddres, const float* __restrict__ zscale, const float* __restrict__ zshift, int LC) {
+  const int cl = threadIdx.x & (LC - 1), rl = threadIdx.x / LC;
+  const int nrl = 256 / LC;
+  const int c4 = blockIdx.x * LC + cl;
+  if (c4 >= C4) return;
   const int C = C4 * 4;
+  const int c = c4 * 4;
   const bool remask = !z && zscale && act != 0;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long r = i / C4;
-    const int c = static_cast<int>(i - r * C4) * 4;
+  const long long rows_per = (rows + gridDim.y - 1) / gridDim.y;
+  const long long rbeg = blockIdx.y * rows_per;
+  const long long rend = rbeg + rows_per < rows ? rbeg + rows_per : rows;
+  const float4 mu = *reinterpret_cast<const float4*>(mean + c);
+  const float4 is = *reinterpret_cast<const float4*>(invstd + c);
+  const float4 ga = gamma ? *reinterpret_cast<const float4*>(gamma + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+  const float4 sg = *reinterpret_cast<const float4*>(sums + c);
+  const float4 sgx = *reinterpret_cast<const float4*>(sums + C + c);
+  float4 zs = make_float4(0.f, 0.f, 0.f, 0.f), zb = zs;
+  if (remask) {
+    zs = *reinterpret_cast<const float4*>(zscale + c);
+    zb = *reinterpret_cast<const float4*>(zshift + c);
+  }
+#pragma unroll 2
+  for (long long r = rbeg + rl; r < rend; r += nrl) {
     float4 g = *reinterpret_cast<const float4*>(dz + r * lddz + c);
     const float4 yy = *reinterpret_cast<const float4*>(y + r * ldy + c);
     if (z) {
@@ -343,17 +363,10 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dz, int lddz, cons
       g.x *= act_bwd_from_out(zz.x, act, slope); g.y *= act_bwd_from_out(zz.y, act, slope);
       g.z *= act_bwd_from_out(zz.z, act, slope); g.w *= act_bwd_from_out(zz.w, act, slope);
     } else if (remask) {
-      const float4 zs = *reinterpret_cast<const float4*>(zscale + c);
-      const float4 zb = *reinterpret_cast<const float4*>(zshift + c);
       g.x *= act_bwd_from_out(fmaf(yy.x, zs.x, zb.x), act, slope); g.y *= act_bwd_from_out(fmaf(yy.y, zs.y, zb.y), act, slope);
       g.z *= act_bwd_from_out(fmaf(yy.z, zs.z, zb.z), act, slope); g.w *= act_bwd_from_out(fmaf(yy.w, zs.w, zb.w), act, slope);
     }
     if (dres) *reinterpret_cast<float4*>(dres + r * lddres + c) = g;
-    const float4 mu = *reinterpret_cast<const float4*>(mean + c);
-    const float4 is = *reinterpret_cast<const float4*>(invstd + c);
-    const float4 ga = gamma ? *reinterpret_cast<const float4*>(gamma + c) : make_float4(1.f, 1.f, 1.f, 1.f);
-    const float4 sg = *reinterpret_cast<const float4*>(sums + c);
-    const float4 sgx = *reinterpret_cast<const float4*>(sums + C + c);
     float4 o;
     o.x = ga.x * is.x * (g.x - sg.x * inv_count - (yy.x - mu.x) * is.x * sgx.x * inv_count);
     o.y = ga.y * is.y * (g.y - sg.y * inv_count - (yy.y - mu.y) * is.y * sgx.y * inv_count);
@@ -645,6 +658,27 @@ extern "C" int cavp_bn_eval_coeffs(const float* gamma, const float* beta, const 
   bn_eval_coeffs_kernel<<<(C + 255) / 256, 256, 0, ST(stream)>>>(gamma, beta, rm, rv, eps, C, scale, shift);
   CAVP_LAUNCH_CHECK();
 }
+// column lanes per 256-thread block for the column-stationary kernels: the candidate that wastes the fewest lanes on
+// the last block (ties: wider); row blocks so that the grid is ~8 blocks per SM
+static int pick_lc(int C4) {
+  int LC = 64, best = -1;
+  for (int cand = 64; cand >= 16; cand >>= 1) {
+    const int util = 1000 * C4 / (((C4 + cand - 1) / cand) * cand);
+    if (util > best) {
+      best = util;
+      LC = cand;
+    }
+  }
+  return LC;
+}
+static dim3 colgrid(long long rows, int C4, int LC) {
+  const int gx = (C4 + LC - 1) / LC, nrl = 256 / LC;
+  long long gy = (rows + 4LL * nrl - 1) / (4LL * nrl);
+  const long long cap = (8LL * NUM_SMS + gx - 1) / gx;
+  if (gy > cap) gy = cap;
+  if (gy < 1) gy = 1;
+  return dim3(gx, static_cast<unsigned>(gy));
+}
 extern "C" int cavp_bn_apply(const float* y, int ldy, const float* scale, const float* shift, const float* res, int ldr,
                              float* out, int ldo, long long rows, int C, int act, float slope, void* stream) {
   if ((C & 3) || (ldy & 3) || (ldo & 3) || (res && (ldr & 3))) return CAVP_ERR_ALIGN;
@@ -659,17 +693,7 @@ extern "C" int cavp_colreduce(const float* dz, int lddz, const float* z, int ldz
   if ((C & 3) || (lddz & 3) || (z && (ldz & 3)) || (y && (ldy & 3)) || (gout && (ldg & 3)) || (ldp & 3))
     return CAVP_ERR_ALIGN;
   const int C4 = C / 4;
-  int LC = 64;  // column lanes per block: the candidate that wastes the fewest lanes on the last block (ties: wider)
-  {
-    int best = -1;
-    for (int cand = 64; cand >= 16; cand >>= 1) {
-      const int util = 1000 * C4 / (((C4 + cand - 1) / cand) * cand);
-      if (util > best) {
-        best = util;
-        LC = cand;
-      }
-    }
-  }
+  const int LC = pick_lc(C4);
   dim3 grid((C4 + LC - 1) / LC, nblk);
   colreduce_kernel<<<grid, 256, 0, ST(stream)>>>(dz, lddz, z, ldz, y, ldy, mean, invstd, rows, C4, act, slope, gout,
                                                  ldg, partials, ldp, zscale, zshift, LC);
@@ -684,9 +708,10 @@ extern "C" int cavp_bn_bwd_apply(const float* dz, int lddz, const float* z, int 
                                  float inv_count, long long rows, int C, int act, float slope, float* dy, int lddy,
                                  float* dres, int lddres, const float* zscale, const float* zshift, void* stream) {
   if ((C & 3) || (lddz & 3) || (ldy & 3) || (lddy & 3)) return CAVP_ERR_ALIGN;
-  bn_bwd_apply_kernel<<<grid_for(rows * (C / 4), 256), 256, 0, ST(stream)>>>(
+  const int LC = pick_lc(C / 4);
+  bn_bwd_apply_kernel<<<colgrid(rows, C / 4, LC), 256, 0, ST(stream)>>>(
       dz, lddz, z, ldz, y, ldy, mean, invstd, gamma, sums, inv_count, rows, C / 4, act, slope, dy, lddy, dres, lddres,
-      zscale, zshift);
+      zscale, zshift, LC);
   CAVP_LAUNCH_CHECK();
 }
 extern "C" int cavp_maxpool_fwd(const float* x, int ldx, float* y, int ldy, int* idx, int n, int h, int w, int c, int k,
