@@ -101,31 +101,61 @@ class ClockSampler(threading.Thread):
 
 
 # ======================================================================================================================
-def cpu_reference_arm(steps, warmup, batch, threads=None):
-    """The reference arithmetic on the host cores: oracle port (torch CPU fp32) of the same train step + optimisers."""
-    from oracle import cavp_oracle as O
+def host_threads():
+    """Host cores this process may use (affinity-aware).  torch.distributed.run exports OMP_NUM_THREADS=1 to its
+    children; the CPU arms override that explicitly so they always use every core the box gives us."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def _oracle_state(device, dtype=torch.float32):
     from oracle import schema
-    if threads:
-        torch.set_num_threads(threads)
-    torch.manual_seed(666)
-    sd = schema.seeded_state(CFG["nc"], CFG["audio"], CFG["in_plane"], seed=0, requires_grad=True)
+    sd = schema.seeded_state(CFG["nc"], CFG["audio"], CFG["in_plane"], seed=0, requires_grad=False)
+    out = {}
+    for k, v in sd.items():
+        v = v.to(device=device, dtype=dtype) if v.is_floating_point() else v.to(device)
+        out[k] = v.requires_grad_(True) if (v.is_floating_point() and "running_" not in k) else v
+    return out
+
+
+def _oracle_stepper(sd, batch, device):
+    """-> step() running the restated trainer body (trainer_cavp_vpo_mono.py:142-193) with torch.optim SGD + Adam."""
+    from oracle import cavp_oracle as O
     leaves = [v for v in sd.values() if v.is_floating_point() and v.requires_grad]
-    audio_params = [v for k, v in sd.items() if k.startswith("audio_backbone.backbone") and v.is_floating_point()]
+    audio_params = [v for k, v in sd.items() if k.startswith("audio_backbone.backbone") and v.is_floating_point()
+                    and v.requires_grad]
     audio_ids = {id(v) for v in audio_params}
     opt_v = torch.optim.SGD([v for v in leaves if id(v) not in audio_ids], lr=1e-3, momentum=0.9, weight_decay=5e-4)
     opt_a = torch.optim.Adam(audio_params, lr=1e-4)
     image, audio, pix, spl = synthetic_batch(batch, 666)
-    b = {"image": image, "audio": audio, "pix_label": pix}
-    times = []
-    for it in range(warmup + steps):
-        t0 = time.perf_counter()
-        opt_v.zero_grad(); opt_a.zero_grad()
+    b = {"image": image.to(device), "audio": audio.to(device), "pix_label": pix.to(device)}
+    spl = spl.to(device)
+
+    def step():
+        opt_v.zero_grad(set_to_none=True)
+        opt_a.zero_grad(set_to_none=True)
         l_ce, l_ctr, *_rest, newbuf = O.train_step_losses(sd, b, spl, dilation_flags=CFG["dilation"],
                                                           audio_kind=CFG["audio"], max_views=CFG["max_views"])
         (l_ce + l_ctr).backward()
-        opt_v.step(); opt_a.step()
+        opt_v.step()
+        opt_a.step()
         for k, v in newbuf.items():
             sd[k] = v
+        return l_ce, l_ctr
+    return step
+
+
+def cpu_reference_arm(steps, warmup, batch, threads=None):
+    """The reference arithmetic on the host cores: oracle port (torch CPU fp32) of the same train step + optimisers."""
+    torch.set_num_threads(threads or host_threads())
+    torch.manual_seed(666)
+    step = _oracle_stepper(_oracle_state("cpu"), batch, "cpu")
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        step()
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
@@ -133,17 +163,104 @@ def cpu_reference_arm(steps, warmup, batch, threads=None):
     return batch / (ms / 1e3), ms, torch.get_num_threads()
 
 
+def gpu_stock_baseline(dev, batch, steps=5, warmup=2):
+    """SURVEY.md 8(d) / BASELINE.md 5.3: the reference arithmetic (oracle port = the same torch ops the reference
+    modules call) under STOCK PyTorch / cuDNN / cuBLAS on this B200, same workload, same step body + torch.optim,
+    timed with CUDA events.  Settings of the reference entry point (main_vpo_mono.py:33-42): cudnn.benchmark = True and
+    torch's defaults, i.e. TF32 allowed for cuDNN convolutions, not for cuBLAS matmuls ("reference_default")."""
+    modes = [("fp32_no_tf32", False, False, None), ("reference_default", True, False, None),
+             ("tf32_all", True, True, None), ("bf16_autocast", True, True, torch.bfloat16)]
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    out = {"what": "oracle port (same torch ops as the reference modules) on cuda, stock PyTorch %s / cuDNN %s, "
+                   "cudnn.benchmark=True, bs%d, %d warm-up + %d timed steps, CUDA events"
+                   % (torch.__version__, torch.backends.cudnn.version(), batch, warmup, steps)}
+    try:
+        torch.backends.cudnn.benchmark = True
+        for name, conv_tf32, mm_tf32, amp in modes:
+            try:
+                torch.backends.cudnn.allow_tf32 = conv_tf32
+                torch.backends.cuda.matmul.allow_tf32 = mm_tf32
+                torch.manual_seed(666)
+                step = _oracle_stepper(_oracle_state(dev), batch, dev)
+                ctx = torch.autocast("cuda", dtype=amp) if amp is not None else None
+
+                def run():
+                    if ctx is None:
+                        return step()
+                    with ctx:
+                        return step()
+                for _ in range(warmup):
+                    run()
+                torch.cuda.synchronize(dev)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(steps):
+                    l_ce, l_ctr = run()
+                e1.record()
+                torch.cuda.synchronize(dev)
+                ms = e0.elapsed_time(e1) / steps
+                out[name] = {"images_per_s": batch / (ms / 1e3), "ms_per_step": ms,
+                             "cudnn_allow_tf32": conv_tf32, "matmul_allow_tf32": mm_tf32,
+                             "autocast": None if amp is None else "bf16", "l_ce": float(l_ce), "l_ctr": float(l_ctr)}
+                del step
+            except Exception as e:  # a stock-library failure must not take the bench line down
+                out[name] = {"error": repr(e)[:200]}
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = saved
+    return out
+
+
+def measure_tf32_peak(dev, seconds=2.0):
+    """TF32 dense matmul peak measured like MEASURED_PEAKS.json measures bf16: torch.matmul 8192^3 with allow_tf32,
+    best of 10 (burst) and back to back for `seconds` (sustained).  3xTF32 (fp32-parity mode) can reach a third of it."""
+    saved = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn(n, n, device=dev)
+        b = torch.randn(n, n, device=dev)
+        for _ in range(3):
+            a @ b
+        torch.cuda.synchronize(dev)
+        best = 1e9
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            a @ b
+            e1.record()
+            torch.cuda.synchronize(dev)
+            best = min(best, e0.elapsed_time(e1))
+        reps = max(10, int(seconds * 1e3 / best))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            a @ b
+        e1.record()
+        torch.cuda.synchronize(dev)
+        sus = e0.elapsed_time(e1) / reps
+        fl = 2.0 * n ** 3
+        return {"tf32_tflops": fl / (best / 1e3) / 1e12, "tf32_tflops_sustained": fl / (sus / 1e3) / 1e12,
+                "how": "torch.matmul fp32 8192^3, allow_tf32=True: best of 10 and back to back for %.0f s" % seconds}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = saved
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    batch = args.cpu_batch
-    value, ms, cores = cpu_reference_arm(args.steps, args.warmup, batch)
-    sample = f"{batch} images per step (bounded sample of the bs32 workload), {args.steps} timed steps"
+    batch = args.cpu_batch or 32  # the same 32 images per step as the GPU arm (configs[1])
+    value, ms, cores = cpu_reference_arm(args.steps, args.warmup, batch, threads=host_threads())
+    sample = (f"{batch} images per step" + ("" if batch == 32 else " (bounded sample of the bs32 workload)") +
+              f", {args.warmup} warm-up + {args.steps} timed steps, {cores} threads "
+              f"(os.cpu_count()={os.cpu_count()}, OMP_NUM_THREADS={os.environ.get('OMP_NUM_THREADS')} overridden)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "per_gpu_batch": 32, "sample_batch": batch},
+            "config": {"workload": WORKLOAD, "per_gpu_batch": 32, "images_per_step": batch,
+                       "note": "reference arithmetic on the host CPU (oracle port: the reference is Python/PyTorch and "
+                               "cannot travel to the GPU box); one CPU replica regardless of --gpus"},
             "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -165,8 +282,10 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # keep stdout to the one JSON line: NCCL prints its version banner (and any INFO the box configures) to stdout
-        os.environ["NCCL_DEBUG"] = os.environ.get("CAVP_NCCL_DEBUG", "WARN")
+        # NCCL's INIT lines (communicator size, NVLS / ring choice) go to stderr: the driver reads the rank count from
+        # them, and stdout stays the one JSON line.  A level set by the caller wins.
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
@@ -324,11 +443,23 @@ def run_ours(args):
                          "ms": gate[0]}
         breakdown = {k: round(v[0], 3) for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:12]}
 
-    cpu = None
+    cpu, stock, tf32_peak = None, None, None
+    if rank == 0 and world == 1 and not args.no_stock_baseline:
+        torch.cuda.empty_cache()
+        tf32_peak = measure_tf32_peak(dev)
+        stock = gpu_stock_baseline(dev, B)
+        if roofline is not None and tf32_peak:
+            ceil3 = tf32_peak["tf32_tflops_sustained"] / 3.0
+            roofline["tf32_peak_measured"] = tf32_peak
+            roofline["frac_of_3xtf32_ceiling"] = roofline["achieved"] / ceil3
+            roofline["note"] += ("; against the TF32 matmul peak measured in this run (sustained / 3 = %.0f TFLOP/s) "
+                                 "the tile kernels reach frac_of_3xtf32_ceiling" % ceil3)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, ms, cores = cpu_reference_arm(2, 1, args.cpu_batch)
+        cb = args.cpu_batch or 8
+        v, ms, cores = cpu_reference_arm(2, 1, cb, threads=host_threads())
         cpu = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
-               "sample": f"oracle port, {args.cpu_batch} images per step, 1 warm-up + 2 timed steps ({ms:.0f} ms/step)"}
+               "sample": f"oracle port, {cb} images per step (bounded sample of the bs32 workload; --impl reference runs "
+                         f"all 32), 1 warm-up + 2 timed steps ({ms:.0f} ms/step), {cores} threads"}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
@@ -345,7 +476,8 @@ def run_ours(args):
                 "gpu_launches": launches_per_step * args.steps,
                 "gpu_launches_per_step": launches_per_step, "host_issue_ms_per_step": host_issue_ms,
                 "roofline": roofline, "attn_roofline": attn_roof, "kernel_ms_top": breakdown,
-                "reference_equiv_tflops": value * FLOPS_PER_IMAGE / 1e12, "cpu_baseline": cpu}
+                "reference_equiv_tflops": value * FLOPS_PER_IMAGE / 1e12, "cpu_baseline": cpu,
+                "gpu_stock_baseline": stock}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -359,8 +491,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="images per GPU")
     ap.add_argument("--prec", type=int, default=2, help="2 = fp32-parity (3xTF32 + promotion), 1 = plain TF32")
-    ap.add_argument("--cpu-batch", type=int, default=4, help="images per CPU reference step (bounded sample)")
+    ap.add_argument("--cpu-batch", type=int, default=None,
+                    help="images per CPU reference step (default: 32 for --impl reference, 8 for the inline cpu_baseline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stock-baseline", action="store_true",
+                    help="skip the stock-PyTorch-on-this-GPU arm (gpu_stock_baseline) and the TF32 peak measurement")
     ap.add_argument("--dump-profile", default=None, help="write the per-launch CUDA-event profile of one step here")
     args = ap.parse_args()
     if args.impl == "reference":

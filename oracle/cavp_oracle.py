@@ -357,10 +357,12 @@ def info_nce(anchors, labels, temperature=0.1, eps=1e-12):
 
 def contrast_loss(embeds_match, gt_match, embeds_shuffle, gt_shuffle, max_views=512, temperature=0.1):
     """contrastive_aud.py:17-37."""
-    sel = contrast_select(gt_match, gt_shuffle, embeds_match.shape[2:], max_views)
+    # the selection is host-side index logic in the reference (CPU randperm); run it on CPU copies of the labels so the
+    # same function also serves embeddings that live on a CUDA device / in fp64 (bench.py gpu_stock_baseline, bs32 tests)
+    sel = contrast_select(gt_match.cpu(), gt_shuffle.cpu(), embeds_match.shape[2:], max_views)
     if sel is None:
-        return torch.tensor([0.0])
-    half, pix, labels = sel
+        return torch.zeros(1, device=embeds_match.device, dtype=embeds_match.dtype)
+    half, pix, labels = (t.to(embeds_match.device) for t in sel)
     em = F.normalize(embeds_match, p=2, dim=1).flatten(2).permute(0, 2, 1).reshape(-1, embeds_match.shape[1])
     es = F.normalize(embeds_shuffle, p=2, dim=1).flatten(2).permute(0, 2, 1).reshape(-1, embeds_shuffle.shape[1])
     anchors = torch.where(half.view(-1, 1) == 0, em[pix], es[pix])

@@ -1,0 +1,159 @@
+"""Parity AT THE BENCHMARKED SIZE: one full train step of BASELINE.json configs[1] (bs32, 224^2, 22 classes, dilation FTT,
+VGG audio - the workload bench.py times) and of configs[2..4] at full size, compared with the oracle
+(oracle/cavp_oracle.py, pinned to the unmodified reference by tests/test_oracle_golden.py) evaluated ON THE GPU:
+
+  * in fp64 - the arbiter: logits / fusion embedding / attention maps / losses within the north-star tolerance (1e-3
+    max-norm relative), argmax bit-exact wherever the fp64 top-2 margin exceeds the tolerance;
+  * in fp32 with TF32 disabled - the reference arithmetic itself.  Its distance to fp64 is the yardstick for the
+    per-tensor END-TO-END gradients: this random-weight, batch-stat-BN network amplifies rounding (ReLU / max-pool
+    decisions flip), so two fp32 implementations can only agree with fp64 as well as fp32 allows.  We require our
+    kernels' per-tensor gradient error to stay within GRAD_RATIO x the fp32 oracle's own error (plus a floor), i.e. the
+    CUDA path is as close to exact arithmetic as stock fp32 PyTorch is.  A dropped or doubled fan-in term would show up
+    as an O(1) error on the affected tensors - far outside this band.
+
+Reference contract: trainer/trainer_cavp_vpo_mono.py:168-191.
+"""
+import json
+import os
+
+import pytest
+import torch
+
+from test_parity_gpu import build_model
+from oracle import schema, seeded
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3          # north_star: 1e-3 relative fp32 tolerance on logits
+GRAD_RATIO = 2.0    # our per-tensor gradient error vs fp64 <= GRAD_RATIO * (fp32 oracle error vs fp64) + GRAD_FLOOR
+GRAD_FLOOR = 1e-3
+
+CONFIGS = {
+    # BASELINE.json configs[1] = the bench workload
+    "cfg1_vpo_ss_ftt22_bs32": dict(B=32, H=224, W=224, nc=22, dilation=(False, True, True), audio="vgg", in_plane=1,
+                                   frames=96, audio_func=False, oracle64=True),
+    "cfg2_avss_fff71_bs32": dict(B=32, H=224, W=224, nc=71, dilation=(False, False, False), audio="vgg", in_plane=1,
+                                 frames=96, audio_func=False, oracle64=True),
+    # 16 clips x 5 frames folded into the batch; fp64 at bs80 would need > 100 GB: fp32 oracle only
+    "cfg3_vpo_ms_t5_bs80": dict(B=80, H=224, W=224, nc=22, dilation=(False, True, True), audio="vgg", in_plane=1,
+                                frames=96, audio_func=False, oracle64=False),
+    "cfg4_msmi_stereo_r18_bs32": dict(B=32, H=224, W=224, nc=22, dilation=(False, True, True), audio="18", in_plane=2,
+                                      frames=300, audio_func=True, oracle64=True),
+}
+
+
+def relmax(a, b):
+    a, b = a.detach().double(), b.detach().double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-300))
+
+
+def oracle_step(cfg, batch, spl, dtype, seed):
+    """The restated trainer body on cuda in `dtype` (TF32 off).  Returns outputs + per-parameter gradients."""
+    from oracle import cavp_oracle as O
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        sd = {}
+        for k, v in schema.seeded_state(cfg["nc"], cfg["audio"], cfg["in_plane"], seed=0).items():
+            v = v.cuda().to(dtype) if v.is_floating_point() else v.cuda()
+            sd[k] = v.requires_grad_(True) if (v.is_floating_point() and "running_" not in k) else v
+        B = cfg["B"]
+        image = batch["image"].cuda().to(dtype)
+        audio = (batch["audio"][:B] if cfg["audio_func"] else batch["audio"]).cuda().to(dtype)
+        pix = batch["pix_label"].cuda()
+        torch.manual_seed(seed)
+        out_cat, ctr_cat, pack, newbuf = O.cavp_forward(
+            sd, image, audio, dilation_flags=cfg["dilation"], audio_kind="vgg" if cfg["audio"] == "vgg" else "resnet18",
+            train=True, shuffle_idx=batch["shuffle_idx"].cuda() if cfg["audio_func"] else None,
+            audio_func=cfg["audio_func"])
+        output = out_cat[:B] + out_cat[B:] * 0.0
+        l_ctr = O.contrast_loss(ctr_cat[:B], batch["pix_label"], ctr_cat[B:], spl, 512)
+        l_ce = O.cross_entropy(output, pix)
+        (l_ce + l_ctr.sum()).backward()
+        res = dict(pred=out_cat.detach(), fusion=ctr_cat.detach(), attn=pack["attn_v"].detach(), l_ce=float(l_ce),
+                   l_ctr=float(l_ctr.sum()), grads={k: v.grad for k, v in sd.items() if v.is_floating_point()
+                                                    and v.requires_grad and v.grad is not None},
+                   buffers={k: v.detach() for k, v in newbuf.items()})
+        return res
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_full_size_step_matches_oracle_on_gpu(name):
+    from cavp_b200.trainer import shuffled_labels, train_step
+    cfg = CONFIGS[name]
+    B = cfg["B"]
+    model = build_model(cfg).train()
+    batch = seeded.synthetic_batch(B, cfg["H"], cfg["W"], cfg["nc"], seed=666, audio_frames=cfg["frames"],
+                                   in_plane=cfg["in_plane"])
+    spl = shuffled_labels(batch["pix_label"], batch["img_label"], batch["shuffle_idx"])
+    audio = batch["audio"][:B] if cfg["audio_func"] else batch["audio"]
+    torch.manual_seed(4321)
+    res = train_step(model, batch["image"].cuda(), audio.cuda(), batch["pix_label"], spl, max_views=512,
+                     shuffle_idx=batch["shuffle_idx"].cuda() if cfg["audio_func"] else None,
+                     audio_func=cfg["audio_func"], keep_outputs=True)
+    torch.cuda.synchronize()
+    ours = dict(pred=res.out_pred, fusion=res.out_fusion.contiguous(), attn=res.attn_v, l_ce=float(res.l_ce),
+                l_ctr=float(res.l_ctr), grads={k: p.grad for k, p in model.named_parameters() if p.grad is not None},
+                buffers={k: v.detach().clone() for k, v in model.state_dict().items() if "running_" in k})
+    res.graph = None
+    del res
+    torch.cuda.empty_cache()
+
+    ref32 = oracle_step(cfg, batch, spl, torch.float32, 4321)
+    exact = oracle_step(cfg, batch, spl, torch.float64, 4321) if cfg["oracle64"] else ref32
+    arb = "fp64" if cfg["oracle64"] else "fp32"
+
+    errs = {k: relmax(ours[k], exact[k]) for k in ("pred", "fusion", "attn")}
+    errs["l_ce"] = abs(ours["l_ce"] - exact["l_ce"]) / abs(exact["l_ce"])
+    errs["l_ctr"] = abs(ours["l_ctr"] - exact["l_ctr"]) / max(abs(exact["l_ctr"]), 1e-12)
+    errs32 = {k: relmax(ref32[k], exact[k]) for k in ("pred", "fusion", "attn")}
+    print(name, "ours vs", arb, {k: "%.2e" % v for k, v in errs.items()},
+          "| fp32 oracle vs", arb, {k: "%.2e" % v for k, v in errs32.items()})
+    for k, v in errs.items():
+        assert v < TOL, (k, v)
+    assert exact["l_ctr"] > 0  # the contrastive term is live at this size
+
+    # argmax masks: bit-exact wherever the exact top-2 margin exceeds the tolerance band
+    ep = exact["pred"]
+    top2 = ep.topk(2, dim=1).values
+    safe = (top2[:, 0] - top2[:, 1]) > 2 * TOL * float(ep.abs().max())
+    am_o, am_e = ours["pred"].argmax(1), ep.argmax(1)
+    assert torch.equal(am_o[safe], am_e[safe])
+    mismatch = float((am_o != am_e).float().mean())
+    print(name, "argmax mismatch rate (inside the margin band) %.2e, safe fraction %.4f" % (mismatch, float(safe.float().mean())))
+    assert mismatch < 1e-3
+
+    for k, v in exact["buffers"].items():
+        if "running_" in k:
+            assert relmax(ours["buffers"][k], v) < TOL, k
+
+    # end-to-end gradients, every tensor
+    rows = []
+    for k, ge in exact["grads"].items():
+        assert k in ours["grads"], k
+        ge = ge.double()
+        den = float(ge.norm().clamp_min(1e-300))
+        e_o = float((ours["grads"][k].double() - ge).norm()) / den
+        e_r = float((ref32["grads"][k].double() - ge).norm()) / den
+        rows.append((k, e_o, e_r))
+    assert set(ours["grads"]) == set(exact["grads"])
+    worst = max(rows, key=lambda r: r[1])
+    ratios = sorted(r[1] / max(r[2], 1e-12) for r in rows)
+    print(name, "grads vs %s: worst ours %.2e (%s; fp32 oracle there %.2e); median ours/fp32-oracle ratio %.2f, max %.2f"
+          % (arb, worst[1], worst[0], worst[2], ratios[len(ratios) // 2], ratios[-1]))
+    dump = os.environ.get("CAVP_PARITY_DUMP")
+    if dump:
+        os.makedirs(dump, exist_ok=True)
+        json.dump({"errs": errs, "errs_fp32_oracle": errs32, "arbiter": arb, "argmax_mismatch": mismatch,
+                   "grads": [{"name": k, "ours": a, "fp32_oracle": b} for k, a, b in rows]},
+                  open(os.path.join(dump, f"parity_{name}.json"), "w"), indent=1)
+    if cfg["oracle64"]:
+        for k, e_o, e_r in rows:
+            assert e_o <= GRAD_RATIO * e_r + GRAD_FLOOR, (k, e_o, e_r)
+    else:  # fp32 arbiter: both sides carry fp32 noise; bound by the noise level the fp64 configs measured
+        for k, e_o, _ in rows:
+            assert e_o < 0.1, (k, e_o)
+    del ours, ref32, exact
+    torch.cuda.empty_cache()
