@@ -271,7 +271,7 @@ def run_reference(args):
 def run_ours(args):
     import torch.distributed as dist
     from cavp_b200.models.cavp_model import CAVP
-    from cavp_b200.parallel import FlatGradBuffer
+    from cavp_b200.parallel import FlatGradBuffer, cavp_buckets
     from cavp_b200.trainer import train_step
 
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -303,7 +303,7 @@ def run_ours(args):
     from cavp_b200.optim import SGD, Adam
     opt_v = SGD(visual_params, lr=1e-3 * world, momentum=0.9, weight_decay=5e-4)
     opt_a = Adam(audio_params, lr=1e-4 * world)
-    flat = FlatGradBuffer(list(model.parameters()), dev) if world > 1 else None
+    flat = FlatGradBuffer(cavp_buckets(model), dev) if world > 1 else None
 
     image_h, audio_h, pix_h, spl_h = synthetic_batch(B, 666 + rank)
     pinned = [t.pin_memory() for t in (image_h, audio_h, pix_h)]
@@ -338,11 +338,8 @@ def run_ours(args):
             stage_inputs()  # next step's copy, overlapping this step's kernels
         opt_v.zero_grad(set_to_none=True)
         opt_a.zero_grad(set_to_none=True)
-        res = train_step(model, im, au, pix_h, spl_h, max_views=CFG["max_views"], assign_grads=(flat is None),
-                         labels_dev=px, profile=profile)
-        if flat is not None:
-            flat.pack(res.param_grads)
-            flat.all_reduce()
+        res = train_step(model, im, au, pix_h, spl_h, max_views=CFG["max_views"], labels_dev=px, profile=profile,
+                         grad_sink=flat)  # N>1: bucketed all-reduce overlapped with the backward pass
         opt_v.step()
         opt_a.step()
         launches[0] += res.launches + 2  # + the two fused optimiser kernels

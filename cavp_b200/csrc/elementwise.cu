@@ -141,7 +141,8 @@ __global__ void bn_finalize_kernel(const PT* __restrict__ partials, int nparts, 
                                    float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
                                    float eps, float* __restrict__ mean_out, float* __restrict__ invstd_out,
                                    float* __restrict__ scale_out, float* __restrict__ shift_out,
-                                   double* __restrict__ sums_io, int sums_mode) {
+                                   double* __restrict__ sums_io, int sums_mode,
+                                   long long* __restrict__ num_batches_tracked) {
   __shared__ double sh1[32][33], sh2[32][33];
   const int ch = blockIdx.x * 32 + threadIdx.x;
   double s1 = 0.0, s2 = 0.0;
@@ -174,15 +175,18 @@ __global__ void bn_finalize_kernel(const PT* __restrict__ partials, int nparts, 
       s1 += sh1[j][threadIdx.x];
       s2 += sh2[j][threadIdx.x];
     }
-    if (sums_mode == 1) {  // only export local sums (SyncBatchNorm: all-reduced by the host side, then mode 2)
+    if (sums_mode == 1) {  // only export local sums + the local count (SyncBatchNorm: all-reduced, then mode 2)
       sums_io[ch] = s1;
       sums_io[C + ch] = s2;
+      if (ch == 0) sums_io[2 * C] = count;
       return;
     }
-    if (sums_mode == 2) {
+    if (sums_mode == 2) {  // global sums and the GLOBAL count come from the all-reduced buffer: no host round trip
       s1 = sums_io[ch];
       s2 = sums_io[C + ch];
+      count = sums_io[2 * C];
     }
+    if (ch == 0 && num_batches_tracked) num_batches_tracked[0] += 1;  // nn.BatchNorm2d bookkeeping, same launch
     const double mean = s1 / count;
     double var = s2 / count - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -333,7 +337,9 @@ bn_bwd_apply_kernel(const float* __restrict__ dz, int lddz, const float* __restr
                     const float* __restrict__ invstd, const float* __restrict__ gamma,
                     const float* __restrict__ sums, float inv_count, long long rows, int C4, int act,
                     float slope, float* __restrict__ dy, int lddy, float* __restrict__ dres,
-                    int lddres, const float* __restrict__ zscale, const float* __restrict__ zshift, int LC) {
+                    int lddres, const float* __restrict__ zscale, const float* __restrict__ zshift, int LC,
+                    const double* __restrict__ count_dev) {
+  if (count_dev) inv_count = static_cast<float>(1.0 / count_dev[0]);  // SyncBatchNorm: the all-reduced global count
   const int cl = threadIdx.x & (LC - 1), rl = threadIdx.x / LC;
   const int nrl = 256 / LC;
   const int c4 = blockIdx.x * LC + cl;
@@ -628,7 +634,7 @@ extern "C" int cavp_gather_rows(const float* src, const long long* idx, float* d
 extern "C" int cavp_bn_finalize(const float* partials, int nparts, int ldstat, int C, double count, const float* gamma,
                                 const float* beta, float* running_mean, float* running_var, float momentum, float eps,
                                 float* mean_out, float* invstd_out, float* scale_out, float* shift_out, double* sums_io,
-                                int sums_mode, void* stream) {
+                                int sums_mode, long long* num_batches_tracked, void* stream) {
   constexpr int S = 16, WS_C = 8192;
   if (sums_mode != 2 && nparts >= 512 && C <= WS_C) {
     // two-stage path; the fp64 workspace is per device and reused by every call (launches of one stream are ordered;
@@ -645,12 +651,12 @@ extern "C" int cavp_bn_finalize(const float* partials, int nparts, int ldstat, i
                                                                                     ws_dev[dev]);
     bn_finalize_kernel<double><<<(C + 31) / 32, dim3(32, 32), 0, ST(stream)>>>(
         ws_dev[dev], S, C, C, count, gamma, beta, running_mean, running_var, momentum, eps, mean_out, invstd_out,
-        scale_out, shift_out, sums_io, sums_mode);
+        scale_out, shift_out, sums_io, sums_mode, num_batches_tracked);
     CAVP_LAUNCH_CHECK();
   }
   bn_finalize_kernel<float><<<(C + 31) / 32, dim3(32, 32), 0, ST(stream)>>>(
       partials, nparts, ldstat, C, count, gamma, beta, running_mean, running_var, momentum, eps, mean_out, invstd_out,
-      scale_out, shift_out, sums_io, sums_mode);
+      scale_out, shift_out, sums_io, sums_mode, num_batches_tracked);
   CAVP_LAUNCH_CHECK();
 }
 extern "C" int cavp_bn_eval_coeffs(const float* gamma, const float* beta, const float* rm, const float* rv, float eps,
@@ -706,12 +712,13 @@ extern "C" int cavp_partials_sum(const float* partials, int nparts, int ldp, int
 extern "C" int cavp_bn_bwd_apply(const float* dz, int lddz, const float* z, int ldz, const float* y, int ldy,
                                  const float* mean, const float* invstd, const float* gamma, const float* sums,
                                  float inv_count, long long rows, int C, int act, float slope, float* dy, int lddy,
-                                 float* dres, int lddres, const float* zscale, const float* zshift, void* stream) {
+                                 float* dres, int lddres, const float* zscale, const float* zshift,
+                                 const double* count_dev, void* stream) {
   if ((C & 3) || (lddz & 3) || (ldy & 3) || (lddy & 3)) return CAVP_ERR_ALIGN;
   const int LC = pick_lc(C / 4);
   bn_bwd_apply_kernel<<<colgrid(rows, C / 4, LC), 256, 0, ST(stream)>>>(
       dz, lddz, z, ldz, y, ldy, mean, invstd, gamma, sums, inv_count, rows, C / 4, act, slope, dy, lddy, dres, lddres,
-      zscale, zshift, LC);
+      zscale, zshift, LC, count_dev);
   CAVP_LAUNCH_CHECK();
 }
 extern "C" int cavp_maxpool_fwd(const float* x, int ldx, float* y, int ldy, int* idx, int n, int h, int w, int c, int k,

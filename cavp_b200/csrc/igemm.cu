@@ -54,11 +54,20 @@ static int make_dy_tmap(CUtensorMap* tm, const float* dy, long long P, int cout)
   return r == CUDA_SUCCESS ? 0 : 1000 + static_cast<int>(r);
 }
 
+// cudaFuncSetAttribute is per device: one process may drive several GPUs (nn.DataParallel, cuda:1 after cuda:0)
+static constexpr int MAX_DEVICES = 64;
+static inline int current_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return (d >= 0 && d < MAX_DEVICES) ? d : 0;
+}
+
 template <int BN, int PREC, int MODE, bool BTMA>
 static int launch_igemm(const IgemmParams& p, const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, cudaStream_t st) {
   using Cfg = TileCfg<BN, PREC>;
   auto kern = igemm_kernel<BN, PREC, MODE, BTMA>;
-  static bool configured = false;
+  static bool configured_dev[MAX_DEVICES] = {};
+  bool& configured = configured_dev[current_device()];
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return static_cast<int>(e);
@@ -74,7 +83,8 @@ template <int BN, int PREC>
 static int launch_igemm_ts(const IgemmParams& p, const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, cudaStream_t st) {
   using Cfg = TsCfg<BN, PREC>;
   auto kern = igemm_ts_kernel<BN, PREC>;
-  static bool configured = false;
+  static bool configured_dev[MAX_DEVICES] = {};
+  bool& configured = configured_dev[current_device()];
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return static_cast<int>(e);
@@ -90,7 +100,8 @@ template <int BN, int PREC>
 static int launch_igemm_ws(const IgemmParams& p, const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, cudaStream_t st) {
   using Cfg = WsCfg<BN, PREC>;
   auto kern = igemm_ws_kernel<BN, PREC>;
-  static bool configured = false;
+  static bool configured_dev[MAX_DEVICES] = {};
+  bool& configured = configured_dev[current_device()];
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return static_cast<int>(e);
@@ -108,7 +119,8 @@ template <int BN, int PREC>
 static int launch_igemm_ws2(const IgemmParams& p, const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, cudaStream_t st) {
   using Cfg = Ws2Cfg<BN, PREC>;
   auto kern = igemm_ws2_kernel<BN, PREC>;
-  static int max_pairs = 0;
+  static int max_pairs_dev[MAX_DEVICES] = {};
+  int& max_pairs = max_pairs_dev[current_device()];
   if (max_pairs == 0) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return static_cast<int>(e);
@@ -136,7 +148,8 @@ template <int PREC>
 static int launch_wgrad2(const IgemmParams& p, const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, cudaStream_t st) {
   using Cfg = Wg2Cfg<PREC>;
   auto kern = igemm_wgrad2_kernel<PREC>;
-  static bool configured = false;
+  static bool configured_dev[MAX_DEVICES] = {};
+  bool& configured = configured_dev[current_device()];
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return static_cast<int>(e);

@@ -16,7 +16,7 @@ __global__ void ce_fwd_kernel(const float* __restrict__ logits, const long long*
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long lab = labels[i];
-    if (lab == ignore_index) continue;
+    if (lab == ignore_index || lab < 0 || lab >= C) continue;  // out-of-range labels never index the logits
     const long long img = i / HW, pix = i - img * HW;
     const float* lp = logits + img * C * HW + pix;
     float mx = -INFINITY;
@@ -60,7 +60,7 @@ __global__ void ce_bwd_kernel(const float* __restrict__ logits, const long long*
     const long long img = i / HW, pix = i - img * HW;
     const float* lp = logits + img * C * HW + pix;
     float* dp = dlogits + img * C * HW + pix;
-    if (lab == ignore_index) {
+    if (lab == ignore_index || lab < 0 || lab >= C) {
       for (int c = 0; c < C; ++c) dp[c * HW] = 0.f;
       continue;
     }
@@ -73,6 +73,109 @@ __global__ void ce_bwd_kernel(const float* __restrict__ logits, const long long*
       const float pr = expf(lp[c * HW] - mx) * inv;
       dp[c * HW] = (pr - (c == lab ? 1.f : 0.f)) * coef;
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------- fused bilinear upsample + CE
+// Training never needs the full-resolution prediction of forward_cls (models/cavp_model.py:138-141) as a tensor: the
+// trainer feeds it straight into CrossEntropyLoss (trainer_cavp_vpo_mono.py:171,187; loss/losser.py:60-62).  These two
+// kernels read only the low-resolution NHWC logits [n][hin][win][ldx] (B*nc*h*w*4 bytes instead of writing and
+// re-reading B*nc*H*W*4 twice): every output pixel takes the bilinear sample (align_corners=False) of every class with
+// the arithmetic of cavp_bilinear_fwd (bilerp), then its log-sum-exp.  The forward keeps the log-sum-exp per output
+// pixel (4 bytes) for the backward.
+__global__ void __launch_bounds__(256)
+upsample_ce_fwd_kernel(const float* __restrict__ x, int ldx, int hin, int win, int hout, int wout, int B, int C,
+                       float sh_, float sw_, const long long* __restrict__ labels, int ignore_index,
+                       float* __restrict__ lse, float* __restrict__ partials) {
+  __shared__ float sh[32];
+  const long long plane = static_cast<long long>(hout) * wout;
+  const long long total = static_cast<long long>(B) * plane;
+  float loss = 0.f, cnt = 0.f;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ox = static_cast<int>(i % wout);
+    const int oy = static_cast<int>((i / wout) % hout);
+    const long long img = i / plane;
+    const Lerp ly = lerp_index(oy, hin, sh_, 0), lx = lerp_index(ox, win, sw_, 0);
+    const float* base = x + img * hin * win * ldx;
+    const float* pa = base + (static_cast<long long>(ly.i0) * win + lx.i0) * ldx;
+    const float* pb = base + (static_cast<long long>(ly.i0) * win + lx.i1) * ldx;
+    const float* pc = base + (static_cast<long long>(ly.i1) * win + lx.i0) * ldx;
+    const float* pd = base + (static_cast<long long>(ly.i1) * win + lx.i1) * ldx;
+    const long long lab = labels[i];
+    float mx = -INFINITY, picked = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float v = bilerp(ly, lx, __ldg(pa + c), __ldg(pb + c), __ldg(pc + c), __ldg(pd + c));
+      mx = fmaxf(mx, v);
+      if (c == lab) picked = v;
+    }
+    float s = 0.f;
+    for (int c = 0; c < C; ++c)
+      s += expf(bilerp(ly, lx, __ldg(pa + c), __ldg(pb + c), __ldg(pc + c), __ldg(pd + c)) - mx);
+    const float l = mx + logf(s);
+    lse[i] = l;
+    if (lab == ignore_index || lab < 0 || lab >= C) continue;
+    loss += l - picked;
+    cnt += 1.f;
+  }
+  const float bl = block_sum(loss, sh);
+  const float bc = block_sum(cnt, sh);
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x * 2] = bl;
+    partials[blockIdx.x * 2 + 1] = bc;
+  }
+}
+// Gather-form backward (deterministic, no atomics): thread = one low-resolution element (img, iy, ix, ch).  It visits
+// the output pixels whose 2x2 footprint touches (iy, ix), recomputes that pixel's class-ch logit, and accumulates
+// w * (softmax - onehot) * gscale / count.  Pad channels (ch >= C) and images >= n_valid get exact zeros, so the
+// low-resolution gradient buffer needs no memset.
+__global__ void __launch_bounds__(256)
+upsample_ce_bwd_kernel(const float* __restrict__ x, int ldx, int hin, int win, int hout, int wout, int n, int n_valid,
+                       int C, int Cpad, float sh_, float sw_, const long long* __restrict__ labels, int ignore_index,
+                       const float* __restrict__ lse, const float* __restrict__ loss_and_count,
+                       const float* __restrict__ gscale, float* __restrict__ dx, int lddx) {
+  const long long total = static_cast<long long>(n) * hin * win * Cpad;
+  const long long plane = static_cast<long long>(hout) * wout;
+  const float coef = (gscale ? gscale[0] : 1.f) / loss_and_count[1];
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(i % Cpad);
+    const int ix = static_cast<int>((i / Cpad) % win);
+    const int iy = static_cast<int>((i / (static_cast<long long>(Cpad) * win)) % hin);
+    const long long img = i / (static_cast<long long>(Cpad) * win * hin);
+    float acc = 0.f;
+    if (img < n_valid && ch < C) {
+      int y_lo = static_cast<int>(floorf((iy - 1 + 0.5f) / sh_ - 0.5f));
+      int y_hi = static_cast<int>(ceilf((iy + 1 + 0.5f) / sh_ - 0.5f));
+      int x_lo = static_cast<int>(floorf((ix - 1 + 0.5f) / sw_ - 0.5f));
+      int x_hi = static_cast<int>(ceilf((ix + 1 + 0.5f) / sw_ - 0.5f));
+      y_lo = max(y_lo - 1, 0); y_hi = min(y_hi + 1, hout - 1);
+      x_lo = max(x_lo - 1, 0); x_hi = min(x_hi + 1, wout - 1);
+      const float* base = x + img * hin * win * ldx + ch;
+      for (int oy = y_lo; oy <= y_hi; ++oy) {
+        const Lerp ly = lerp_index(oy, hin, sh_, 0);
+        const float wy = (ly.i0 == iy ? ly.w0 : 0.f) + (ly.i1 == iy ? ly.w1 : 0.f);
+        if (wy == 0.f) continue;
+        const float* r0 = base + static_cast<long long>(ly.i0) * win * ldx;
+        const float* r1 = base + static_cast<long long>(ly.i1) * win * ldx;
+        for (int ox = x_lo; ox <= x_hi; ++ox) {
+          const Lerp lx = lerp_index(ox, win, sw_, 0);
+          const float wx = (lx.i0 == ix ? lx.w0 : 0.f) + (lx.i1 == ix ? lx.w1 : 0.f);
+          if (wx == 0.f) continue;
+          const long long o = img * plane + static_cast<long long>(oy) * wout + ox;
+          const long long lab = labels[o];
+          if (lab == ignore_index || lab < 0 || lab >= C) continue;
+          const float v = bilerp(ly, lx, __ldg(r0 + static_cast<long long>(lx.i0) * ldx),
+                                 __ldg(r0 + static_cast<long long>(lx.i1) * ldx),
+                                 __ldg(r1 + static_cast<long long>(lx.i0) * ldx),
+                                 __ldg(r1 + static_cast<long long>(lx.i1) * ldx));
+          const float pr = expf(v - lse[o]);
+          acc += wy * wx * (pr - (ch == lab ? 1.f : 0.f));
+        }
+      }
+      acc *= coef;
+    }
+    dx[((img * hin + iy) * win + ix) * static_cast<long long>(lddx) + ch] = acc;
   }
 }
 
@@ -216,6 +319,28 @@ extern "C" int cavp_ce_bwd(const float* logits, const long long* labels, int B, 
                            const float* loss_and_count, const float* gscale, float* dlogits, void* stream) {
   ce_bwd_kernel<<<grid_for(static_cast<long long>(B) * HW, 256, 16), 256, 0, ST(stream)>>>(
       logits, labels, B, C, HW, ignore_index, loss_and_count, gscale, dlogits);
+  CAVP_LAUNCH_CHECK();
+}
+extern "C" int cavp_upsample_ce_fwd(const float* x, int ldx, int hin, int win, int hout, int wout, int B, int C,
+                                    const long long* labels, int ignore_index, float* lse, float* partials,
+                                    float* loss_and_count, void* stream) {
+  if (!x || !labels || !lse || !partials || !loss_and_count) return CAVP_ERR_NULL;
+  if (B <= 0 || C <= 0 || hin <= 0 || win <= 0 || hout <= 0 || wout <= 0 || ldx < C) return CAVP_ERR_ARG;
+  const int nb = cavp_ce_nblocks(B, static_cast<long long>(hout) * wout);
+  upsample_ce_fwd_kernel<<<nb, 256, 0, ST(stream)>>>(x, ldx, hin, win, hout, wout, B, C, lerp_scale(hin, hout, 0),
+                                                     lerp_scale(win, wout, 0), labels, ignore_index, lse, partials);
+  ce_finish_kernel<<<1, 256, 0, ST(stream)>>>(partials, nb, loss_and_count);
+  CAVP_LAUNCH_CHECK();
+}
+extern "C" int cavp_upsample_ce_bwd(const float* x, int ldx, int hin, int win, int hout, int wout, int n, int n_valid,
+                                    int C, int Cpad, const long long* labels, int ignore_index, const float* lse,
+                                    const float* loss_and_count, const float* gscale, float* dx, int lddx,
+                                    void* stream) {
+  if (!x || !labels || !lse || !loss_and_count || !dx) return CAVP_ERR_NULL;
+  if (n <= 0 || n_valid < 0 || n_valid > n || C <= 0 || Cpad < C || ldx < C || lddx < Cpad) return CAVP_ERR_ARG;
+  upsample_ce_bwd_kernel<<<grid_for(static_cast<long long>(n) * hin * win * Cpad, 256, 16), 256, 0, ST(stream)>>>(
+      x, ldx, hin, win, hout, wout, n, n_valid, C, Cpad, lerp_scale(hin, hout, 0), lerp_scale(win, wout, 0), labels,
+      ignore_index, lse, loss_and_count, gscale, dx, lddx);
   CAVP_LAUNCH_CHECK();
 }
 extern "C" int cavp_l2norm_gather(const float* f, int ld, const long long* pix, int A, int C, float* anchors, int lda,

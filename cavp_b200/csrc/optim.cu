@@ -127,6 +127,32 @@ split_multi_kernel(const SplitTensor* __restrict__ table, const int2* __restrict
   }
 }
 
+// ---- many small device-to-device copies in ONE launch (gradients that were not written straight into the flat
+// all-reduce buffer: BatchNorm / LayerNorm / bias gradients, re-packed stems).  Table rows {src, dst, n}.
+struct CopyTensor {
+  const float* src;
+  float* dst;
+  long long n;
+};
+static_assert(sizeof(CopyTensor) == 24, "table row layout");
+
+__global__ void __launch_bounds__(OPT_THREADS)
+copy_multi_kernel(const CopyTensor* __restrict__ table, const int2* __restrict__ work, int nwork) {
+  for (int wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
+    const int2 w = work[wi];
+    const CopyTensor t = table[w.x];
+    const long long off = static_cast<long long>(w.y) * OPT_CHUNK;
+    const int n = static_cast<int>(t.n - off < OPT_CHUNK ? t.n - off : OPT_CHUNK);
+    const float* src = t.src + off;
+    float* dst = t.dst + off;
+    const uintptr_t al = reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst);
+    const int n4 = (al & 15) == 0 ? (n >> 2) : 0;
+    for (int i = threadIdx.x; i < n4; i += OPT_THREADS)
+      reinterpret_cast<float4*>(dst)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+    for (int i = n4 * 4 + threadIdx.x; i < n; i += OPT_THREADS) dst[i] = src[i];
+  }
+}
+
 static int opt_grid(int nwork) {
   const int cap = NUM_SMS * 8;
   return nwork < cap ? (nwork < 1 ? 1 : nwork) : cap;
@@ -168,5 +194,14 @@ extern "C" int cavp_split_tf32_multi(const void* table, const int* work, int nwo
   if ((reinterpret_cast<uintptr_t>(table) & 7) || (reinterpret_cast<uintptr_t>(work) & 7)) return CAVP_ERR_ALIGN;
   split_multi_kernel<<<opt_grid(nwork), OPT_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const SplitTensor*>(table), reinterpret_cast<const int2*>(work), nwork);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int cavp_copy_multi(const void* table, const int* work, int nwork, void* stream) {
+  if (!table || !work) return CAVP_ERR_NULL;
+  if (nwork <= 0) return 0;
+  if ((reinterpret_cast<uintptr_t>(table) & 7) || (reinterpret_cast<uintptr_t>(work) & 7)) return CAVP_ERR_ALIGN;
+  copy_multi_kernel<<<opt_grid(nwork), OPT_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const CopyTensor*>(table), reinterpret_cast<const int2*>(work), nwork);
   return static_cast<int>(cudaGetLastError());
 }

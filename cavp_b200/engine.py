@@ -207,8 +207,11 @@ class WeightSplitCache:
 
 
 class Graph:
-    def __init__(self, device, prec=2, train=True, sync_bn_group=None):
+    def __init__(self, device, prec=2, train=True, sync_bn_group=None, grad_sink=None):
         self.device = device
+        # grad_sink: a cavp_b200.parallel.FlatGradBuffer - weight-gradient kernels write straight into its views
+        self.grad_sink = grad_sink
+        self.callbacks = {}  # name -> callable, fired by the matching tape marker during backward()
         self.prec = prec
         self.train = train
         self.tape = []
@@ -304,6 +307,27 @@ class Graph:
                 self.call("cavp_zero", root.grad.buf.data_ptr(), root.grad.buf.numel() * 4)
                 fresh = False
         return self.grad_of(a), (not fresh)
+
+    def mark(self, name):
+        """Tape marker: during backward(), `callbacks[name]` runs once every op recorded AFTER this point has finished
+        its backward (used to launch a gradient bucket's all-reduce while the rest of the backward still runs)."""
+        if self.train:
+            def fire():
+                cb = self.callbacks.get(name)
+                if cb is not None:
+                    cb()
+            self.tape.append(fire)
+
+    def weight_grad_buffer(self, wr, co, K):
+        """[co, K] K-major buffer for a weight gradient: the parameter's own view inside the flat all-reduce buffer when
+        its memory format is exactly what the kernel writes (Linear, channels_last conv), else a fresh tensor."""
+        sink = self.grad_sink
+        if (sink is not None and wr.kind in ("linear", "cl") and wr.cout_eff == wr.cout
+                and id(wr.param) not in self.param_grads):
+            v = sink.view_of(wr.param)
+            if v is not None:
+                return (v if wr.kind == "linear" else v.permute(0, 2, 3, 1)).reshape(co, K)
+        return self.empty(co, K)
 
     def add_param_grad(self, p, g):
         key = id(p)
@@ -517,7 +541,7 @@ class Graph:
                 if res is not None and res.needs_grad:
                     self.accumulate_grad(res, g, res_mod, res_div)
                 if wr.param.requires_grad:
-                    dwk = self.empty(co, K)
+                    dwk = self.weight_grad_buffer(wr, co, K)
                     wsplits = self.wgrad_splits(M, co, K)
                     if wsplits > 1:
                         self.call("cavp_zero", dwk.data_ptr(), dwk.numel() * 4)
@@ -564,21 +588,24 @@ class Graph:
         tail = (bn.weight.data_ptr(), bn.bias.data_ptr(), bn.running_mean.data_ptr(), bn.running_var.data_ptr(),
                 momentum, bn.eps, coeffs[0].data_ptr(), coeffs[1].data_ptr(), coeffs[2].data_ptr(),
                 coeffs[3].data_ptr())
+        nbt = bn.num_batches_tracked.data_ptr() if bn.num_batches_tracked is not None else 0
+        count_dev, sync_sums = 0, None
         if sync:
+            # SyncBatchNorm (main_vpo_mono.py:130): local fp64 sums + local count -> ONE all-reduce -> global statistics.
+            # The global count stays on the device (finalize mode 2 and the backward read it there): no host sync.
             import torch.distributed as dist
             sums = self.empty(2 * C + 1, dtype=torch.float64)
-            self.call("cavp_bn_finalize", *head, count, *tail, sums.data_ptr(), 1)
-            sums[2 * C] = count
+            self.call("cavp_bn_finalize", *head, count, *tail, sums.data_ptr(), 1, 0)
             dist.all_reduce(sums, group=self.sync_bn_group)
-            count = float(sums[2 * C].item())
-            self.call("cavp_bn_finalize", *head, count, *tail, sums.data_ptr(), 2)
+            self.call("cavp_bn_finalize", *head, count, *tail, sums.data_ptr(), 2, nbt)
+            count_dev = sums.data_ptr() + 8 * 2 * C
+            sync_sums = sums
         else:
-            self.call("cavp_bn_finalize", *head, count, *tail, 0, 0)
-        bn.num_batches_tracked += 1
+            self.call("cavp_bn_finalize", *head, count, *tail, 0, 0, nbt)
         self.call("cavp_bn_apply", y.ptr, y.ld, coeffs[2].data_ptr(), coeffs[3].data_ptr(),
                   0 if res is None else res.ptr, 0 if res is None else res.ld, z.ptr, z.ld, y.rows, C, act, LEAKY_SLOPE)
 
-        def bwd():
+        def bwd(sync_sums=sync_sums):  # (keeps the all-reduced statistics buffer alive: count_dev points into it)
             dz = self.grad_of(z)
             if dz is None:
                 return
@@ -613,7 +640,7 @@ class Graph:
             self.call("cavp_bn_bwd_apply", dz.ptr, dz.ld, 0 if zin is None else zin.ptr, 0 if zin is None else zin.ld,
                       y.ptr, y.ld, coeffs[0].data_ptr(), coeffs[1].data_ptr(), bn.weight.data_ptr(), sums.data_ptr(),
                       1.0 / count, M, C, act, LEAKY_SLOPE, dy.ptr, dy.ld, 0 if tgt is None else tgt.ptr,
-                      0 if tgt is None else tgt.ld, zs, zb)
+                      0 if tgt is None else tgt.ld, zs, zb, count_dev)
             if tmp is not None:
                 self.add_act(dres, tmp)
         self.tape.append(bwd)

@@ -176,7 +176,9 @@ class _CEFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, logits, labels, ignore_index):
         logits = logits.contiguous()
-        labels = labels.contiguous()
+        if labels.dtype.is_floating_point or labels.dtype == torch.bool:
+            raise RuntimeError("CrossEntropyLoss: class-index labels must be an integer tensor")
+        labels = labels.to(torch.int64).contiguous()  # the kernels read int64; other integer widths are widened here
         B, C = logits.shape[:2]
         HW = logits[0, 0].numel()
         g = Graph(logits.device, train=True)

@@ -505,7 +505,12 @@ class CAVP(nn.Module):
         train = g.train
         x = _input_nhwc(g, image, 4)
         feats = backbone_forward(g, self.backbone.backbone, x)
+        # tape markers for the bucketed gradient all-reduce (cavp_b200/parallel.py:cavp_buckets): the backward pass runs
+        # decoder -> fusion -> audio backbone -> DeepLab head -> ResNet, so the audio bucket is complete when the tape
+        # is back at "audio_grads_done" and everything but the ResNet at "head_grads_done"
+        g.mark("head_grads_done")
         fea_v = forward_feature(g, self.segment, feats)
+        g.mark("audio_grads_done")
         a = _input_nhwc(g, audio, pad4(audio.shape[1]))
         if self.audio_kind == "vgg":
             fea_a = vgg_forward(g, self.audio_backbone.backbone, a)

@@ -77,9 +77,18 @@ class _FusedBase(torch.optim.Optimizer):
             if p.dtype != torch.float32 or not p.is_cuda:
                 raise RuntimeError("cavp_b200.optim: parameters must be fp32 CUDA tensors")
             st = self.state[p]
+            # state loaded from a torch.optim checkpoint (the reference saves both optimisers' state_dicts,
+            # engine/engine.py:93-94): `step` arrives as a per-parameter tensor and the moment buffers in the
+            # checkpoint's NCHW-contiguous strides - normalise both once, on first use
+            if "step" in st and not isinstance(st["step"], int):
+                st["step"] = int(float(st["step"]))
             for name in state_names:
                 if name not in st:
                     st[name] = self._dense_like(p)
+                elif not same_layout(st[name], p) or st[name].dtype != p.dtype or st[name].device != p.device:
+                    fixed = torch.empty_like(p, memory_format=torch.preserve_format)
+                    fixed.copy_(st[name])  # plumbing copy into the parameter's own layout
+                    st[name] = fixed
             gp = 0
             if g is not None:
                 if g.is_sparse:
@@ -92,9 +101,6 @@ class _FusedBase(torch.optim.Optimizer):
                 gp = g.data_ptr()
                 st["step"] = st.get("step", 0) + 1
             s = [st[name] for name in state_names]
-            for t in s:
-                if not same_layout(t, p):
-                    raise RuntimeError("optimizer state layout differs from its parameter")
             rows.append((p.data_ptr(), gp, s[0].data_ptr(), s[1].data_ptr() if len(s) > 1 else 0, p.numel()))
             fl[i, 0], fl[i, 1] = lrs[i], wds[i]
         host[:, :5] = torch.tensor(rows, dtype=torch.int64)

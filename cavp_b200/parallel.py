@@ -1,28 +1,47 @@
-"""Data-parallel plumbing: one process per GPU, the batch sharded across ranks, ONE gradient all-reduce per step.
+"""Data-parallel plumbing: one process per GPU, the batch sharded across ranks, gradients averaged over NCCL.
 
-The reference wraps the model in DDP (main_vpo_mono.py:131-141: bucketed all-reduce from autograd hooks).  Here the
-gradients of a step are packed into a single flat fp32 buffer (parameter order = model.parameters()) and reduced with
-one NCCL all-reduce (average, DDP semantics) over NVLink/NVSwitch; `p.grad` are views into the flat buffer, so the
-optimisers read the reduced values in place.  Parameters that never receive gradients (cross_att.pos_embed_*,
-audio_backbone.cls_head.* - the reason the reference needs find_unused_parameters=True) are left out of the buffer.
+The reference wraps the model in DDP (main_vpo_mono.py:131-141: bucketed all-reduce fired from autograd hooks while the
+backward is still running).  Here the gradients of a step live in ONE flat fp32 buffer made of a few contiguous
+buckets; the weight-gradient kernels write straight into it (`p.grad` are views, the optimisers read the reduced
+values in place), and each bucket's all-reduce (average, DDP semantics) is launched the moment the backward tape has
+passed the last op that contributes to it - the audio backbone (63 % of the gradient bytes) is complete after the
+first quarter of the backward pass, so most of the exchange overlaps the ResNet backward.  Parameters that never
+receive gradients (cross_att.pos_embed_*, audio_backbone.cls_head.* - the reason the reference needs
+find_unused_parameters=True) are left out of the buffer.
 """
 import torch
 import torch.distributed as dist
 
+from . import _C
+
 
 class FlatGradBuffer:
+    """`params`: a list of parameters (one bucket) or a list of lists (buckets, each contiguous in the flat buffer)."""
+
     def __init__(self, params, device=None):
-        self.params = [p for p in params if p.requires_grad]
+        buckets = params if params and isinstance(params[0], (list, tuple)) else [list(params)]
+        self.params, self.bucket_of, self.bucket_range, self.offsets = [], {}, [], []
+        n = 0
+        for b, plist in enumerate(buckets):
+            start = n
+            for p in plist:
+                if not p.requires_grad or id(p) in self.bucket_of:
+                    continue
+                self.bucket_of[id(p)] = b
+                self.params.append(p)
+                self.offsets.append(n)
+                n += (p.numel() + 3) // 4 * 4  # every view starts 16-byte aligned (vectorised kernels write into it)
+            self.bucket_range.append((start, n))
         device = device if device is not None else self.params[0].device
-        self.offsets, n = [], 0
-        for p in self.params:
-            self.offsets.append(n)
-            n += p.numel()
         self.numel = n
         self.flat = torch.zeros(n, dtype=torch.float32, device=device)
+        self.index = {id(p): i for i, p in enumerate(self.params)}
+        self.views = [self._make_view(i) for i in range(len(self.params))]
         self.used = [False] * len(self.params)
+        self._pending = []
+        self._copy_cache = None
 
-    def view_for(self, i):
+    def _make_view(self, i):
         p = self.params[i]
         v = self.flat[self.offsets[i]:self.offsets[i] + p.numel()]
         if p.dim() == 4 and p.is_contiguous(memory_format=torch.channels_last) and not p.is_contiguous():
@@ -30,31 +49,131 @@ class FlatGradBuffer:
             return v.view(n, h, w, c).permute(0, 3, 1, 2)  # same memory format as the parameter
         return v.view(p.shape)
 
-    def pack(self, grads):
-        """grads: dict id(param) -> gradient tensor (any strides).  Copies into the flat buffer and points p.grad at
-        the views.  Parameters without a gradient keep p.grad = None (and contribute zeros to the collective)."""
+    def view_for(self, i):
+        return self.views[i]
+
+    def view_of(self, p):
+        """Gradient view (the parameter's shape and memory format) inside the flat buffer, or None."""
+        i = self.index.get(id(p))
+        return None if i is None else self.views[i]
+
+    def bucket_tensor(self, b):
+        lo, hi = self.bucket_range[b]
+        return self.flat[lo:hi]
+
+    # ------------------------------------------------------------------------------------------------ filling
+    def pack(self, grads, bucket=None):
+        """grads: dict id(param) -> gradient tensor.  Gradients the kernels already wrote into their view are left
+        alone; every other one is copied by ONE table-driven kernel launch (cavp_copy_multi) when the buffer lives on a
+        CUDA device.  Points p.grad at the views; parameters without a gradient keep p.grad = None and contribute
+        zeros to the collective.  `bucket`: only the parameters of that bucket."""
+        todo = []
         for i, p in enumerate(self.params):
+            if bucket is not None and self.bucket_of[id(p)] != bucket:
+                continue
             g = grads.get(id(p))
+            v = self.views[i]
             if g is None:
                 if self.used[i]:
-                    self.view_for(i).zero_()
+                    v.zero_()
+                    self.used[i] = False
                 continue
-            v = self.view_for(i)
-            v.copy_(g)
+            if g.data_ptr() != v.data_ptr():
+                todo.append((i, g))
             p.grad = v
             self.used[i] = True
-
-    def all_reduce(self, group=None, average=True):
-        """ONE collective for the whole step.  NCCL: AVG in-switch when available; gloo (CPU tests): SUM then scale."""
-        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        if not todo:
             return
+        if not self.flat.is_cuda:
+            for i, g in todo:
+                self.views[i].copy_(g)
+            return
+        keep, rows = [], []
+        for i, g in todo:
+            v = self.views[i]
+            if g.shape != v.shape or g.stride() != v.stride() or g.dtype != torch.float32:
+                g2 = torch.empty_like(self.params[i], memory_format=torch.preserve_format)
+                g2.copy_(g)  # plumbing copy into the parameter's layout (rare: re-packed stems, padded classifier)
+                g = g2
+            keep.append(g)
+            rows.append((g.data_ptr(), v.data_ptr(), g.numel()))
+        chunk = _C.query("cavp_opt_chunk_elems")
+        work = [(r, c) for r, (_, _, n) in enumerate(rows) for c in range((n + chunk - 1) // chunk)]
+        table = torch.tensor(rows, dtype=torch.int64).pin_memory().to(self.flat.device, non_blocking=True)
+        workt = torch.tensor(work, dtype=torch.int32).reshape(-1, 2).pin_memory().to(self.flat.device, non_blocking=True)
+        _C.call("cavp_copy_multi", table.data_ptr(), workt.data_ptr(), len(work),
+                torch.cuda.current_stream(self.flat.device).cuda_stream)
+        for t in keep + [table, workt]:
+            t.record_stream(torch.cuda.current_stream(self.flat.device))
+
+    # ------------------------------------------------------------------------------------------------ collectives
+    def _reduce(self, t, group, average, async_op):
         world = dist.get_world_size(group)
         if average and dist.get_backend(group) == "nccl":
-            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group)
-        else:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
-            if average:
-                self.flat.div_(world)
+            return dist.all_reduce(t, op=dist.ReduceOp.AVG, group=group, async_op=async_op), None
+        w = dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+        return w, (1.0 / world if average else None)
+
+    def all_reduce_bucket(self, b, group=None, average=True):
+        """Launch bucket b's all-reduce now, asynchronously: the collective waits for the kernels already queued on
+        the current stream (the gradients of this bucket) and then runs beside whatever is queued next."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return
+        t = self.bucket_tensor(b)
+        if t.numel() == 0:
+            return
+        work, scale = self._reduce(t, group, average, async_op=True)
+        self._pending.append((b, work, scale))
+
+    def begin_step(self):
+        self._flushed = set()
+
+    def flush_bucket(self, b, grads, group=None, average=True):
+        """Bucket b is complete (the backward tape passed its marker): pack what was not produced in place and start
+        its all-reduce.  Idempotent within a step."""
+        flushed = self.__dict__.setdefault("_flushed", set())
+        if b in flushed:
+            return
+        flushed.add(b)
+        self.pack(grads, bucket=b)
+        self.all_reduce_bucket(b, group, average)
+
+    def finish(self, grads, group=None, average=True):
+        """End of the backward pass: flush the remaining buckets and make the current stream wait for all of them."""
+        for b in range(len(self.bucket_range)):
+            self.flush_bucket(b, grads, group, average)
+        self.wait()
+
+    def wait(self):
+        """Make the current stream wait for every launched bucket (call before the optimisers read p.grad)."""
+        for b, work, scale in self._pending:
+            work.wait()
+            if scale is not None:
+                self.bucket_tensor(b).mul_(scale)
+        done = {b for b, _, _ in self._pending}
+        self._pending = []
+        return done
+
+    def all_reduce(self, group=None, average=True):
+        """Reduce every bucket that has not been launched yet, then wait for all of them."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return
+        launched = {b for b, _, _ in self._pending}
+        for b in range(len(self.bucket_range)):
+            if b not in launched:
+                self.all_reduce_bucket(b, group, average)
+        self.wait()
+
+
+def cavp_buckets(model):
+    """Bucket order = the order in which the backward pass completes them (cavp_b200.models.cavp_model.build_graph
+    records the matching tape markers): 0 audio backbone, 1 decoder + fusion + projector + DeepLab head, 2 ResNet."""
+    m = model.module if hasattr(model, "module") else model
+    audio = list(m.audio_backbone.parameters())
+    backbone = list(m.backbone.parameters())
+    taken = {id(p) for p in audio + backbone}
+    head = [p for p in m.parameters() if id(p) not in taken]
+    return [audio, head, backbone]
 
 
 def shard_batch(global_batch, rank, world):

@@ -36,7 +36,7 @@ class StepResult:
 
 def train_step(model, image, audio, pix_label, shuffle_pix_label, *, temperature=0.1, ignore_index=255, max_views=512,
                shuffle_idx=None, audio_func=False, assign_grads=True, keep_outputs=False, sel=None, labels_dev=None,
-               profile=None):
+               profile=None, grad_sink=None):
     """forward + CE + ContrastLoss + backward.  Gradients land in `p.grad` (DDP-style callers all-reduce them
     afterwards, see cavp_b200.parallel).  Returns a StepResult; losses are device tensors (no host sync here)."""
     if not image.is_cuda:
@@ -45,8 +45,15 @@ def train_step(model, image, audio, pix_label, shuffle_pix_label, *, temperature
     dev = image.device
     B, _, H, W = image.shape
     nc = m.num_classes
-    g = Graph(dev, prec=m.prec, train=True, sync_bn_group=m._sync_group())
+    g = Graph(dev, prec=m.prec, train=True, sync_bn_group=m._sync_group(), grad_sink=grad_sink)
     g.profile = profile
+    if grad_sink is not None:
+        # data-parallel mode (cavp_b200.parallel): gradients are produced inside the flat buffer and each bucket's
+        # all-reduce starts as soon as the backward tape has passed it (DDP-style overlap, main_vpo_mono.py:131-141)
+        grad_sink.begin_step()
+        if len(grad_sink.bucket_range) == 3:  # cavp_buckets(): audio | head + fusion | ResNet
+            g.callbacks["audio_grads_done"] = lambda: grad_sink.flush_bucket(0, g.param_grads)
+            g.callbacks["head_grads_done"] = lambda: grad_sink.flush_bucket(1, g.param_grads)
     g.use_weight_cache(m)
     if labels_dev is None:
         labels_dev = pix_label.to(dev, torch.int64, non_blocking=True)
@@ -63,26 +70,45 @@ def train_step(model, image, audio, pix_label, shuffle_pix_label, *, temperature
         gpix = (pix + half * (B * fusion.h * fusion.w)).pin_memory().to(dev, non_blocking=True)
         labels_sel = labels.pin_memory().to(dev, non_blocking=True)
     rows = fusion.n
-    # forward_cls: full-resolution prediction for all rows (the reference returns it, cavp_model.py:138-141)
-    pred = g.upsample_to_nchw(logits, nc, H, W)
-    # CE on output_cat[:B] + output_cat[B:]*0.0  ==  CE on the first B images (value and gradient)
-    ce = ce_forward(g, pred.data_ptr(), labels_dev, B, nc, H * W, ignore_index)
+    # forward_cls + CrossEntropyLoss.  CE on output_cat[:B] + output_cat[B:]*0.0 == CE on the first B images (value
+    # and gradient).  Callers that want the full-resolution prediction back (keep_outputs) get it materialised for all
+    # rows, as the reference returns it (cavp_model.py:138-141); otherwise the upsample is fused into the loss kernels
+    # and [2B, nc, H, W] is never written.
+    pred = None
+    if keep_outputs:
+        pred = g.upsample_to_nchw(logits, nc, H, W)
+        ce = ce_forward(g, pred.data_ptr(), labels_dev, B, nc, H * W, ignore_index)
+    else:
+        lse = g.empty(B * H * W)
+        partials = g.empty(_C.query("cavp_ce_nblocks", B, H * W), 2)
+        ce = g.empty(2)
+        g.work(nbytes=4.0 * B * logits.h * logits.w * logits.ld + 12.0 * B * H * W)
+        g.call("cavp_upsample_ce_fwd", logits.ptr, logits.ld, logits.h, logits.w, H, W, B, nc, labels_dev.data_ptr(),
+               ignore_index, lse.data_ptr(), partials.data_ptr(), ce.data_ptr())
     nce = None
     if sel is not None:
         nce = InfoNCE(g, [(fusion.ptr, fusion.ld, gpix, fusion.c)], labels_sel, temperature)
 
     # ---- backward
-    dpred = g.empty(B, nc, H, W)
-    g.call("cavp_ce_bwd", pred.data_ptr(), labels_dev.data_ptr(), B, nc, H * W, ignore_index, ce.data_ptr(), 0,
-           dpred.data_ptr())
-    g.upsample_to_nchw_backward(logits, nc, dpred, n_valid=B)
+    if keep_outputs:
+        dpred = g.empty(B, nc, H, W)
+        g.call("cavp_ce_bwd", pred.data_ptr(), labels_dev.data_ptr(), B, nc, H * W, ignore_index, ce.data_ptr(), 0,
+               dpred.data_ptr())
+        g.upsample_to_nchw_backward(logits, nc, dpred, n_valid=B)
+    else:
+        dlog, accumulate = g.grad_target(logits)
+        assert not accumulate
+        g.call("cavp_upsample_ce_bwd", logits.ptr, logits.ld, logits.h, logits.w, H, W, logits.n, B, nc, logits.c,
+               labels_dev.data_ptr(), ignore_index, lse.data_ptr(), ce.data_ptr(), 0, dlog.ptr, dlog.ld)
     if nce is not None:
         dfus, accumulate = g.grad_target(fusion)
         if not accumulate:
             g.zero_act(dfus)
         nce.backward(None, [(dfus.ptr, dfus.ld)])
     g.backward()
-    if assign_grads:
+    if grad_sink is not None:
+        grad_sink.finish(g.param_grads)  # p.grad = views of the (averaged) flat buffer
+    elif assign_grads:
         for p in m.parameters():
             gr = g.param_grads.get(id(p))
             if gr is not None:

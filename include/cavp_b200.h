@@ -85,12 +85,14 @@ int cavp_gather_rows(const float* src, const long long* idx, float* dst, int nro
 
 /* ---- BatchNorm (nn.BatchNorm2d, eps 1e-5, momentum 0.1: encoder_decoder.py:10-11, resnet.py:64-72) --------------
  * finalize: reduce the igemm `stats` partials -> mean, invstd, scale = gamma*invstd, shift = beta - mean*scale, and the
- * running-stat update (unbiased variance).  sums_mode: 0 = local statistics; 1 = only export fp64 [2][C] sums to
- * sums_io (SyncBatchNorm: the host all-reduces them, main_vpo_mono.py:130); 2 = take sums from sums_io. */
+ * running-stat update (unbiased variance; num_batches_tracked += 1 in the same launch when the pointer is given).
+ * sums_mode: 0 = local statistics; 1 = only export the fp64 sums [2][C] and the local count to sums_io [2*C + 1]
+ * (SyncBatchNorm, main_vpo_mono.py:130: the caller all-reduces that buffer); 2 = take the sums AND the count from
+ * sums_io (the global count never visits the host). */
 int cavp_bn_finalize(const float* partials, int nparts, int ldstat, int C, double count, const float* gamma,
                      const float* beta, float* running_mean, float* running_var, float momentum, float eps,
                      float* mean_out, float* invstd_out, float* scale_out, float* shift_out, double* sums_io,
-                     int sums_mode, void* stream);
+                     int sums_mode, long long* num_batches_tracked, void* stream);
 int cavp_bn_eval_coeffs(const float* gamma, const float* beta, const float* rm, const float* rv, float eps, int C,
                         float* scale, float* shift, void* stream);
 /* out = act(y*scale + shift (+ res))   (BN apply + ReLU / LeakyReLU(0.01) + Bottleneck residual, resnet.py:86-96) */
@@ -108,7 +110,8 @@ int cavp_partials_sum(const float* partials, int nparts, int ldp, int C, int nk,
 int cavp_bn_bwd_apply(const float* dz, int lddz, const float* z, int ldz, const float* y, int ldy, const float* mean,
                       const float* invstd, const float* gamma, const float* sums, float inv_count, long long rows, int C,
                       int act, float slope, float* dy, int lddy, float* dres, int lddres, const float* zscale,
-                      const float* zshift, void* stream);
+                      const float* zshift, const double* count_dev, void* stream);
+/* ^ count_dev != NULL: 1/count is taken from device memory (the all-reduced count of SyncBatchNorm) instead of inv_count */
 
 /* ---- pooling (F.max_pool2d resnet.py:189 / vgg.py:30; ASPP global pooling encoder_decoder.py:158-164;
  *      AdaptiveMaxPool2d audio_network.py:24) ------------------------------------------------------------------- */
@@ -155,6 +158,20 @@ int cavp_ce_fwd(const float* logits, const long long* labels, int B, int C, long
                 float* partials, float* loss_and_count, void* stream);
 int cavp_ce_bwd(const float* logits, const long long* labels, int B, int C, long long HW, int ignore_index,
                 const float* loss_and_count, const float* gscale, float* dlogits, void* stream);
+/* Fused forward_cls upsample + CrossEntropyLoss for training (models/cavp_model.py:138-141 -> trainer_cavp_vpo_mono.py
+ * :171,187 -> loss/losser.py:60-62): x = low-resolution NHWC logits [n][hin][win][ldx]; the bilinear (align_corners =
+ * False) full-resolution logits are evaluated on the fly with the arithmetic of cavp_bilinear_fwd and never written.
+ * fwd: the first B images; labels int64 [B][hout][wout]; lse [B*hout*wout] (log-sum-exp per output pixel, kept for the
+ * backward); partials [cavp_ce_nblocks(B, hout*wout)][2]; loss_and_count = {mean loss, #valid pixels}.
+ * bwd: dx [n][hin][win][lddx] receives d loss / d x for channels < C, exact zeros for pad channels [C, Cpad) and for
+ * images >= n_valid (no memset needed); gather form, deterministic.  Labels outside [0, C) other than ignore_index are
+ * treated as ignored (they never index the logits). */
+int cavp_upsample_ce_fwd(const float* x, int ldx, int hin, int win, int hout, int wout, int B, int C,
+                         const long long* labels, int ignore_index, float* lse, float* partials, float* loss_and_count,
+                         void* stream);
+int cavp_upsample_ce_bwd(const float* x, int ldx, int hin, int win, int hout, int wout, int n, int n_valid, int C,
+                         int Cpad, const long long* labels, int ignore_index, const float* lse,
+                         const float* loss_and_count, const float* gscale, float* dx, int lddx, void* stream);
 int cavp_l2norm_gather(const float* f, int ld, const long long* pix, int A, int C, float* anchors, int lda,
                        float* inv_norm, void* stream);
 int cavp_l2norm_scatter_bwd(const float* danchors, const float* anchors, int lda, const float* inv_norm,
@@ -176,6 +193,10 @@ int cavp_opt_chunk_elems(void);
 int cavp_sgd_multi(const void* table, const int* work, int nwork, float momentum, void* stream);
 int cavp_adam_multi(const void* table, const int* work, int nwork, double beta1, double beta2, double eps,
                     double bias_correction1, double bias_correction2, void* stream);
+/* dst[i] = src[i] for a table of tensors in ONE launch: 24-byte rows {const float* src; float* dst; long long n}, same
+ * (row, chunk) work list.  Packs the gradients that were not produced in place into the flat all-reduce buffer
+ * (cavp_b200/parallel.py; the reference's DDP reducer copies into its buckets the same way, main_vpo_mono.py:131-141). */
+int cavp_copy_multi(const void* table, const int* work, int nwork, void* stream);
 
 /* ---- eval epilogue (csrc/metrics.cu) -----------------------------------------------------------
  * Replace torch.max(logits, 1) + 3x torch.histc (utils/eval_utils.py:73-97, MIoU) and argmax -> .cpu().numpy() ->

@@ -318,3 +318,58 @@ def test_contrast_loss_empty_selection_returns_zero():
     gt = torch.zeros(2, 32, 32, dtype=torch.int64, device="cuda")
     out = ContrastLoss(0.1, 255, 512)(em, gt, em, gt)
     assert out.shape == (1,) and float(out) == 0.0
+
+
+@pytest.mark.parametrize("nc,hin,win,hout,wout", [(22, 14, 14, 56, 56), (71, 9, 13, 36, 52), (2, 7, 5, 23, 17)])
+def test_fused_upsample_cross_entropy_matches_torch(nc, hin, win, hout, wout):
+    """cavp_upsample_ce_fwd / bwd (the train-step path that never writes the full-resolution logits) against
+    F.interpolate(align_corners=False) + F.cross_entropy(ignore_index=255) in fp64, on the first B of 2B rows
+    (trainer_cavp_vpo_mono.py:171: the shuffled half is weighted by zero)."""
+    from cavp_b200 import _C
+    from cavp_b200.engine import pad4
+    torch.manual_seed(9)
+    B, rows, cp = 3, 6, pad4(nc)
+    x = torch.randn(rows, cp, hin, win, dtype=torch.double); x[:, nc:] = 0
+    xr = x[:B, :nc].clone().requires_grad_(True)
+    labels = torch.randint(0, nc, (B, hout, wout)); labels[0, :3, :4] = 255; labels[1, 5, 5] = 255
+    ref = F.cross_entropy(F.interpolate(xr, size=(hout, wout), mode="bilinear", align_corners=False), labels,
+                          ignore_index=255)
+    ref.backward()
+    g = _g()
+    xa = to_act(g, x)
+    lab = labels.cuda()
+    lse = g.empty(B * hout * wout)
+    partials = g.empty(_C.query("cavp_ce_nblocks", B, hout * wout), 2)
+    out = g.empty(2)
+    g.call("cavp_upsample_ce_fwd", xa.ptr, xa.ld, hin, win, hout, wout, B, nc, lab.data_ptr(), 255, lse.data_ptr(),
+           partials.data_ptr(), out.data_ptr())
+    assert abs(float(out[0]) - float(ref)) < TOL * abs(float(ref))
+    assert int(out[1]) == int((labels != 255).sum())
+    dx, acc = g.grad_target(xa)
+    dx.buf.fill_(float("nan"))  # the kernel must write every element (pad channels and rows >= B as zeros)
+    g.call("cavp_upsample_ce_bwd", xa.ptr, xa.ld, hin, win, hout, wout, rows, B, nc, cp, lab.data_ptr(), 255,
+           lse.data_ptr(), out.data_ptr(), 0, dx.ptr, dx.ld)
+    got = back(dx)
+    assert rel_err(got[:B, :nc], xr.grad) < TOL
+    assert float(got[:B, nc:].abs().max() if cp > nc else 0.0) == 0.0 and float(got[B:].abs().max()) == 0.0
+    # same loss value as the materialised path (bilinear kernel + CE kernel) to fp32 rounding of the reduction order
+    p = g.upsample_to_nchw(xa, nc, hout, wout)
+    from cavp_b200.loss import ce_forward
+    ce2 = ce_forward(g, p.data_ptr(), lab, B, nc, hout * wout, 255)
+    assert abs(float(ce2[0]) - float(out[0])) < 1e-6 * abs(float(out[0]))
+
+
+def test_cross_entropy_out_of_range_labels_are_ignored_not_dereferenced():
+    from cavp_b200.loss import CrossEntropyLoss
+    torch.manual_seed(8)
+    logits = torch.randn(2, 5, 9, 9, dtype=torch.double, requires_grad=True)
+    labels = torch.randint(0, 5, (2, 9, 9))
+    bad = labels.clone(); bad[0, 0, :4] = 254; bad[1, 2, 2] = -3
+    ok = labels.clone(); ok[0, 0, :4] = 255; ok[1, 2, 2] = 255
+    ref = F.cross_entropy(logits, ok, ignore_index=255)
+    ref.backward()
+    lg = logits.detach().float().cuda().requires_grad_(True)
+    loss = CrossEntropyLoss(255)(lg, bad.to(torch.int32).cuda())  # int32 labels are widened, not reinterpreted
+    loss.backward()
+    assert abs(float(loss) - float(ref)) < TOL * abs(float(ref))
+    assert rel_err(lg.grad, logits.grad) < TOL

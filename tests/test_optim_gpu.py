@@ -77,3 +77,50 @@ def test_adam_matches_torch():
         assert rel_err(b, a) < 2e-6
         assert rel_err(ours.state[b]["exp_avg"], ref.state[a]["exp_avg"]) < 2e-6
         assert rel_err(ours.state[b]["exp_avg_sq"], ref.state[a]["exp_avg_sq"]) < 2e-6
+
+
+def test_resume_from_torch_optim_checkpoint():
+    """engine/engine.py:93-94 saves optimizer_v / optimizer_a state_dicts of torch.optim.SGD / Adam: per-parameter
+    tensor `step`, NCHW-contiguous moment buffers (our conv parameters are channels_last).  Loading such a checkpoint
+    into the fused optimisers and continuing must track torch step for step."""
+    from cavp_b200.optim import SGD, Adam
+    for make_ref, make_ours, keys, tol in (
+            (lambda ps: torch.optim.SGD(ps, lr=3e-3, momentum=0.9, weight_decay=5e-4),
+             lambda ps: SGD(ps, lr=3e-3, momentum=0.9, weight_decay=5e-4), ("momentum_buffer",), 1e-6),
+            (lambda ps: torch.optim.Adam(ps, lr=1e-3), lambda ps: Adam(ps, lr=1e-3), ("exp_avg", "exp_avg_sq"), 2e-6)):
+        # the checkpoint is written by torch.optim on NCHW-contiguous parameters (the reference's layout)
+        pa = [torch.nn.Parameter(p.detach().contiguous()) for p in make_params(2)]
+        pb = make_params(2)
+        ref = make_ref(pa)
+        for step in range(2):
+            set_grads(pa, 30 + step)
+            for p in pa:
+                p.grad = p.grad.contiguous()
+            ref.step()
+        ckpt = torch.load(__import__("io").BytesIO(_dumps(ref.state_dict())), weights_only=False)
+        with torch.no_grad():
+            for a, b in zip(pa, pb):
+                b.copy_(a)
+        ours = make_ours(pb)
+        ours.load_state_dict(ckpt)
+        for step in range(2, 5):
+            set_grads(pa, 30 + step)
+            for p in pa:
+                p.grad = p.grad.contiguous()
+            set_grads(pb, 30 + step)
+            ref.step()
+            ours.step()
+        torch.cuda.synchronize()
+        for a, b in zip(pa, pb):
+            assert rel_err(b, a) < tol
+            for k in keys:
+                assert rel_err(ours.state[b][k], ref.state[a][k]) < tol
+            assert ours.state[b][k].stride() == b.stride()
+            assert ours.state[b]["step"] == 5 if "step" in ref.state[a] else True
+
+
+def _dumps(obj):
+    import io
+    buf = io.BytesIO()
+    torch.save(obj, buf)
+    return buf.getvalue()

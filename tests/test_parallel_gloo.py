@@ -31,6 +31,30 @@ def _worker(rank, world, port, ret):
     ok &= bool(torch.allclose(conv.weight.grad, torch.arange(conv.weight.numel(), dtype=torch.float32).view_as(conv.weight) * 1.5))
     ok &= conv.weight.grad.is_contiguous(memory_format=torch.channels_last)
     ok &= shard_batch(64, rank, world) == (rank * 32, rank * 32 + 32)
+    # bucketed buffer: per-bucket flush (pack + asynchronous all-reduce) in completion order, then finish()
+    bb = FlatGradBuffer([[lin.weight, lin.bias], [conv.weight, conv.bias, unused]])
+    assert bb.bucket_range[0][0] == 0 and bb.bucket_range[1][0] == bb.bucket_range[0][1]
+    assert all(o % 4 == 0 for o in bb.offsets)
+    bb.begin_step()
+    # a gradient produced in place (what the weight-gradient kernels do through Graph.weight_grad_buffer)
+    bb.view_of(lin.weight).fill_(float(rank + 1))
+    g2 = {id(lin.weight): bb.view_of(lin.weight), id(lin.bias): torch.full_like(lin.bias, float(2 * rank)),
+          id(conv.weight): grads[id(conv.weight)], id(conv.bias): torch.full_like(conv.bias, float(rank + 3))}
+    bb.flush_bucket(0, g2)
+    bb.flush_bucket(0, g2)  # idempotent
+    bb.finish(g2)
+    ok &= bool(torch.allclose(lin.weight.grad, torch.full_like(lin.weight, 1.5)))
+    ok &= bool(torch.allclose(lin.bias.grad, torch.full_like(lin.bias, 1.0)))
+    ok &= bool(torch.allclose(conv.bias.grad, torch.full_like(conv.bias, 3.5)))
+    ok &= bool(torch.allclose(conv.weight.grad, torch.arange(conv.weight.numel(), dtype=torch.float32).view_as(conv.weight) * 1.5))
+    ok &= lin.weight.grad.data_ptr() == bb.view_of(lin.weight).data_ptr()
+    # next step: a parameter that gets no gradient any more contributes zeros
+    bb.begin_step()
+    g3 = dict(g2); del g3[id(conv.bias)]
+    conv.bias.grad = None
+    bb.view_of(lin.weight).fill_(float(rank + 1))
+    bb.finish(g3)
+    ok &= conv.bias.grad is None and float(bb.view_of(conv.bias).abs().max()) == 0.0
     ret[rank] = ok
     dist.destroy_process_group()
 
