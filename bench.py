@@ -201,7 +201,8 @@ def gpu_stock_baseline(dev, batch, steps=5, warmup=2):
                 ms = e0.elapsed_time(e1) / steps
                 out[name] = {"images_per_s": batch / (ms / 1e3), "ms_per_step": ms,
                              "cudnn_allow_tf32": conv_tf32, "matmul_allow_tf32": mm_tf32,
-                             "autocast": None if amp is None else "bf16", "l_ce": float(l_ce), "l_ctr": float(l_ctr)}
+                             "autocast": None if amp is None else "bf16", "l_ce": float(l_ce.detach()),
+                             "l_ctr": float(l_ctr.detach().sum())}
                 del step
             except Exception as e:  # a stock-library failure must not take the bench line down
                 out[name] = {"error": repr(e)[:200]}

@@ -60,6 +60,48 @@ __global__ void transpose_kernel(const float* __restrict__ src, float* __restric
     }
   }
 }
+// The same transpose + TF32 split for EVERY dgrad weight operand of a model in one launch (the per-layer launches were
+// launch-bound: ~140 kernels of a few microseconds per step).  Table rows mirror the int64[9] the host packs
+// (cavp_b200/engine.py:WeightSplitCache); a work item is one 32 x 32 tile of one batch (= filter tap) of one tensor.
+struct TsTensor {
+  const float* src;
+  float* hi;
+  float* lo;
+  int rows, cols;
+  long long src_ld, dst_ld, src_bs, dst_bs;
+  int tiles_c, tiles_r;
+};
+static_assert(sizeof(TsTensor) == 72, "table row layout");
+
+__global__ void __launch_bounds__(256)
+transpose_split_multi_kernel(const TsTensor* __restrict__ table, const int2* __restrict__ work, int nwork) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
+    const int2 w = work[wi];
+    const TsTensor t = table[w.x];
+    const int per = t.tiles_c * t.tiles_r;
+    const int z = w.y / per, rem = w.y - z * per;
+    const int c0 = (rem % t.tiles_c) * 32, r0 = (rem / t.tiles_c) * 32;
+    const float* s = t.src + z * t.src_bs;
+    __syncthreads();  // the previous item's reads of `tile` are done
+    for (int j = ty; j < 32; j += 8) {
+      const int r = r0 + j, cc = c0 + tx;
+      tile[j][tx] = (r < t.rows && cc < t.cols) ? __ldg(s + r * t.src_ld + cc) : 0.f;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+      const int cc = c0 + j, r = r0 + tx;
+      if (cc < t.cols && r < t.rows) {
+        const float v = tile[tx][j];
+        const float h = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
+        const long long o = z * t.dst_bs + cc * t.dst_ld + r;
+        t.hi[o] = h;
+        t.lo[o] = __uint_as_float((__float_as_uint(v - h) + 0x1000u) & 0xFFFFE000u);
+      }
+    }
+  }
+}
 __global__ void add_inplace_kernel(float* __restrict__ dst, const float* __restrict__ src, long long n4, float alpha) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -619,6 +661,15 @@ extern "C" int cavp_transpose_split(const float* src, float* hi, float* lo, int 
   if (!src || !hi || !lo) return CAVP_ERR_NULL;
   dim3 grid((cols + 31) / 32, (rows + 31) / 32, batch), block(32, 8);
   transpose_kernel<<<grid, block, 0, ST(stream)>>>(src, hi, lo, rows, cols, src_ld, dst_ld, src_bs, dst_bs);
+  CAVP_LAUNCH_CHECK();
+}
+extern "C" int cavp_transpose_split_multi(const void* table, const int* work, int nwork, void* stream) {
+  if (!table || !work) return CAVP_ERR_NULL;
+  if (nwork <= 0) return 0;
+  if ((reinterpret_cast<uintptr_t>(table) & 7) || (reinterpret_cast<uintptr_t>(work) & 7)) return CAVP_ERR_ALIGN;
+  const int grid = nwork < NUM_SMS * 16 ? nwork : NUM_SMS * 16;
+  transpose_split_multi_kernel<<<grid, 256, 0, ST(stream)>>>(static_cast<const TsTensor*>(table),
+                                                             reinterpret_cast<const int2*>(work), nwork);
   CAVP_LAUNCH_CHECK();
 }
 extern "C" int cavp_add_inplace(float* dst, const float* src, long long n, float alpha, void* stream) {

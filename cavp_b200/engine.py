@@ -126,12 +126,20 @@ class WeightRef:
     def operand_t(self):
         """[hi | lo] split of the transposed operand [Cin][taps][Cout_eff] for the data-gradient GEMM (one kernel)."""
         if self._wt_split is None:
+            cache = self.g.wcache
+            if cache is not None and self.kind in ("linear", "cl") and self.cout_eff == self.cout:
+                hit = cache.operand_t(self.param)
+                if hit is not None:
+                    self._wt_split = hit[0]
+                    self._wt_lo_off = hit[1]
+                    return self._wt_split, self._wt_lo_off
             taps = self.r * self.s
             sp = self.g.empty(2, self.cin, taps * self.cout_eff)
             self.g.call("cavp_transpose_split", self.wk.data_ptr(), sp[0].data_ptr(), sp[1].data_ptr(), self.cout_eff,
                         self.cin, taps * self.cin, taps * self.cout_eff, taps, self.cin, self.cout_eff)
-            self._wt_split = sp
-        return self._wt_split, self._wt_split[0].numel()
+            self._wt_split = sp[0]
+            self._wt_lo_off = sp[0].numel()
+        return self._wt_split, self._wt_lo_off
 
     def transposed(self):
         """[Cin][taps][Cout_eff] for the data-gradient GEMM."""
@@ -182,6 +190,41 @@ class WeightSplitCache:
         self.table = torch.tensor(rows, dtype=torch.int64).to(device)
         self.work = torch.tensor(work, dtype=torch.int32).reshape(-1, 2).to(device)
         self.lo_off = total  # lo = hi + total elements for every weight
+        self._t = None  # transposed operands of the data-gradient GEMMs: built on the first training step
+
+    def _build_transposed(self):
+        """[Cin][taps][Cout] hi | lo splits of every weight (the dgrad B operand), one persistent buffer + one table."""
+        total = self.lo_off
+        buf = torch.empty(2, total, device=self.device, dtype=torch.float32)
+        views, rows, work, off = {}, [], [], 0
+        for i, p in enumerate(self.params):
+            n = p.numel()
+            cout = p.shape[0]
+            cin = p.shape[1]
+            taps = n // (cout * cin)
+            hi, lo = buf[0, off:off + n], buf[1, off:off + n]
+            views[id(p)] = hi.view(cin, taps * cout)
+            tiles_c, tiles_r = (cin + 31) // 32, (cout + 31) // 32
+            rows.append((p.data_ptr(), hi.data_ptr(), lo.data_ptr(), cout | (cin << 32), taps * cin, taps * cout, cin,
+                         cout, tiles_c | (tiles_r << 32)))
+            work.extend((i, t) for t in range(taps * tiles_c * tiles_r))
+            off += n
+        self._t = {"buf": buf, "views": views,
+                   "table": torch.tensor(rows, dtype=torch.int64).to(self.device),
+                   "work": torch.tensor(work, dtype=torch.int32).reshape(-1, 2).to(self.device)}
+
+    def refresh_transposed(self, g):
+        if self._t is None:
+            self._build_transposed()
+        g.call("cavp_transpose_split_multi", self._t["table"].data_ptr(), self._t["work"].data_ptr(),
+               self._t["work"].shape[0])
+
+    def operand_t(self, param):
+        """(hi tensor [Cin, taps*Cout], lo offset in elements) or None"""
+        if self._t is None:
+            return None
+        v = self._t["views"].get(id(param))
+        return None if v is None else (v, self.lo_off)
 
     @staticmethod
     def eligible(model):
@@ -236,6 +279,8 @@ class Graph:
             cache = WeightSplitCache(params, self.device)
             model.__dict__["_cavp_wsplit"] = cache
         self.call("cavp_split_tf32_multi", cache.table.data_ptr(), cache.work.data_ptr(), cache.work.shape[0])
+        if self.train:
+            cache.refresh_transposed(self)  # the dgrad operands of every layer, one launch
         self.wcache = cache
 
     # ------------------------------------------------------------------ small helpers

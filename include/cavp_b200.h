@@ -78,6 +78,10 @@ int cavp_transpose(const float* src, float* dst, int rows, int cols, long long s
 /* the same transpose writing the TF32 split of the result (hi, lo): the dgrad weight operand in one pass */
 int cavp_transpose_split(const float* src, float* hi, float* lo, int rows, int cols, long long src_ld, long long dst_ld,
                          int batch, long long src_bs, long long dst_bs, void* stream);
+/* cavp_transpose_split for every dgrad weight operand of a model in ONE launch: table = device array of 72-byte rows
+ * {const float* src; float* hi; float* lo; int rows, cols; long long src_ld, dst_ld, src_bs, dst_bs; int tiles_c,
+ * tiles_r}; work = (row, tile) int pairs, tile enumerating (batch, 32-row tile, 32-column tile). */
+int cavp_transpose_split_multi(const void* table, const int* work, int nwork, void* stream);
 int cavp_add_inplace(float* dst, const float* src, long long n, float alpha, void* stream);
 /* dst[i] = src[idx[i]] (fea_a[shuffle_idx], models/cavp_model.py:171) or, accumulate_scatter=1, dst[idx[i]] += src[i] */
 int cavp_gather_rows(const float* src, const long long* idx, float* dst, int nrows, int c, int accumulate_scatter,

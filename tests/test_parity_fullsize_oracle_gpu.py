@@ -24,8 +24,8 @@ from oracle import schema, seeded
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-3          # north_star: 1e-3 relative fp32 tolerance on logits
-GRAD_RATIO = 2.0    # our per-tensor gradient error vs fp64 <= GRAD_RATIO * (fp32 oracle error vs fp64) + GRAD_FLOOR
-GRAD_FLOOR = 1e-3
+GRAD_RATIO = 1.0    # our per-tensor gradient error vs fp64 <= GRAD_RATIO * (fp32 oracle error vs fp64) + GRAD_FLOOR
+GRAD_FLOOR = 1e-3   # (measured on B200, profiles/r02_parity_fullsize.txt: ours / fp32-oracle error ratio median 0.4-0.5, max 0.65)
 
 CONFIGS = {
     # BASELINE.json configs[1] = the bench workload
@@ -33,9 +33,9 @@ CONFIGS = {
                                    frames=96, audio_func=False, oracle64=True),
     "cfg2_avss_fff71_bs32": dict(B=32, H=224, W=224, nc=71, dilation=(False, False, False), audio="vgg", in_plane=1,
                                  frames=96, audio_func=False, oracle64=True),
-    # 16 clips x 5 frames folded into the batch; fp64 at bs80 would need > 100 GB: fp32 oracle only
+    # 16 clips x 5 frames folded into the batch
     "cfg3_vpo_ms_t5_bs80": dict(B=80, H=224, W=224, nc=22, dilation=(False, True, True), audio="vgg", in_plane=1,
-                                frames=96, audio_func=False, oracle64=False),
+                                frames=96, audio_func=False, oracle64=True),
     "cfg4_msmi_stereo_r18_bs32": dict(B=32, H=224, W=224, nc=22, dilation=(False, True, True), audio="18", in_plane=2,
                                       frames=300, audio_func=True, oracle64=True),
 }
@@ -102,13 +102,16 @@ def test_full_size_step_matches_oracle_on_gpu(name):
     torch.cuda.empty_cache()
 
     ref32 = oracle_step(cfg, batch, spl, torch.float32, 4321)
-    exact = oracle_step(cfg, batch, spl, torch.float64, 4321) if cfg["oracle64"] else ref32
-    arb = "fp64" if cfg["oracle64"] else "fp32"
+    for k in ("pred", "fusion", "attn"):  # park the big fp32-oracle outputs on the host while the fp64 oracle runs
+        ref32[k] = ref32[k].cpu()
+    torch.cuda.empty_cache()
+    exact = oracle_step(cfg, batch, spl, torch.float64, 4321)
+    arb = "fp64"
 
     errs = {k: relmax(ours[k], exact[k]) for k in ("pred", "fusion", "attn")}
     errs["l_ce"] = abs(ours["l_ce"] - exact["l_ce"]) / abs(exact["l_ce"])
     errs["l_ctr"] = abs(ours["l_ctr"] - exact["l_ctr"]) / max(abs(exact["l_ctr"]), 1e-12)
-    errs32 = {k: relmax(ref32[k], exact[k]) for k in ("pred", "fusion", "attn")}
+    errs32 = {k: relmax(ref32[k].cuda(), exact[k]) for k in ("pred", "fusion", "attn")}
     print(name, "ours vs", arb, {k: "%.2e" % v for k, v in errs.items()},
           "| fp32 oracle vs", arb, {k: "%.2e" % v for k, v in errs32.items()})
     for k, v in errs.items():
@@ -149,11 +152,7 @@ def test_full_size_step_matches_oracle_on_gpu(name):
         json.dump({"errs": errs, "errs_fp32_oracle": errs32, "arbiter": arb, "argmax_mismatch": mismatch,
                    "grads": [{"name": k, "ours": a, "fp32_oracle": b} for k, a, b in rows]},
                   open(os.path.join(dump, f"parity_{name}.json"), "w"), indent=1)
-    if cfg["oracle64"]:
-        for k, e_o, e_r in rows:
-            assert e_o <= GRAD_RATIO * e_r + GRAD_FLOOR, (k, e_o, e_r)
-    else:  # fp32 arbiter: both sides carry fp32 noise; bound by the noise level the fp64 configs measured
-        for k, e_o, _ in rows:
-            assert e_o < 0.1, (k, e_o)
+    for k, e_o, e_r in rows:
+        assert e_o <= GRAD_RATIO * e_r + GRAD_FLOOR, (k, e_o, e_r)
     del ours, ref32, exact
     torch.cuda.empty_cache()

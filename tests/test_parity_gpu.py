@@ -17,13 +17,15 @@ TOL = 1e-3  # north_star tolerance
 # arithmetic itself (oracle in fp32 vs the same oracle in fp64, tools/grad_sensitivity.py ->
 # tests/golden/grad_sensitivity.json) differs by 3-4e-2 relative L2 per tensor and up to 9e-3 in norm, because tiny
 # forward perturbations flip ReLU / max-pool decisions.  Two independent fp32 implementations can therefore only agree
-# to a small multiple of that self-discrepancy: end-to-end we allow 4x the fixture's measured value; elementwise
-# gradient parity is asserted per op (2e-5) in tests/test_ops_gpu.py.
+# to a small multiple of that self-discrepancy: against the fp32 goldens we allow 2x the fixture's measured value (our
+# error + the reference's own); elementwise gradient parity is asserted per op (2e-5) in tests/test_ops_gpu.py, and
+# tests/test_parity_fullsize_oracle_gpu.py compares every gradient tensor with an fp64 oracle on the GPU, where the
+# kernels must be at least as close to exact arithmetic as stock fp32 PyTorch is.
 import json
 import os
 
 _SENS = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "grad_sensitivity.json")))
-GRAD_FACTOR = 4.0
+GRAD_FACTOR = 2.0
 
 
 def grad_tols(name):
@@ -158,11 +160,15 @@ def test_module_autograd_path_equals_train_step():
 # ---------------------------------------------------------------------------------------------------------------
 # edge cases against the oracle on the same seeded inputs (the reference itself has no tests: SURVEY.md section 4)
 # ---------------------------------------------------------------------------------------------------------------
-def _oracle_train(cfg, batch, spl, seed):
+def _oracle_train(cfg, batch, spl, seed, dtype=torch.float64):
+    """The oracle in fp64 (CPU) is the arbiter for the tiny, badly conditioned edge shapes: against the fp32 oracle a
+    comparison also contains the fp32 oracle's own rounding noise, which is as large as ours here."""
     from oracle import cavp_oracle as O
     sd = schema.seeded_state(cfg["nc"], cfg["audio"], cfg["in_plane"], seed=0, requires_grad=True)
+    sd = {k: (v.detach().to(dtype).requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    b = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in batch.items()}
     torch.manual_seed(seed)
-    return O.train_step_losses(sd, batch, spl, dilation_flags=cfg["dilation"], audio_kind=cfg["audio"],
+    return O.train_step_losses(sd, b, spl, dilation_flags=cfg["dilation"], audio_kind=cfg["audio"],
                                max_views=cfg["max_views"])
 
 
@@ -188,14 +194,12 @@ def test_train_step_edge_shapes_match_oracle(cfg):
     else:
         assert float(res.l_ctr) == 0.0  # no class reached max_views pixels: reference returns tensor([0.])
     print(cfg["H"], cfg["W"], {k: "%.2e" % v for k, v in errs.items()})
-    # Tiny batches / 5x7 feature maps make the batch-stat BN chain even more ill-conditioned than the golden fixtures
-    # (observed 5e-4 .. 1e-3 against the fp32 oracle, run-to-run spread from atomics included), so the train-mode
-    # edge cases use 3e-3; the same shapes are checked at 1e-4 in eval mode below, where nothing amplifies.
+    # north-star tolerance against exact (fp64) arithmetic; the same shapes are checked at 1e-4 in eval mode below
     for k, v in errs.items():
-        assert v < 3e-3, (k, v)
+        assert v < TOL, (k, v)
     sd = model.state_dict()
     for k, v in newbuf.items():
-        assert rel_err(sd[k].float(), v.float()) < 2e-3, k
+        assert rel_err(sd[k].float(), v.float()) < TOL, k
 
 
 @pytest.mark.parametrize("cfg", [
