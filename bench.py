@@ -32,10 +32,31 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-CFG = dict(nc=22, dilation=(False, True, True), audio="vgg", in_plane=1, H=224, W=224, frames=96, max_views=512)
-WORKLOAD = "configs[1]: ResNet-50 + VGGish CAVP fwd+bwd bs32/GPU, synthetic VPO-SS shapes (22 cls, dilation FTT), fp32"
+# BASELINE.json configs[1] (the headline: fp32, VPO-SS shapes) and configs[2] (AVSBench-Semantics shapes, bf16 loop)
+CONFIGS = {
+    1: dict(cfg=dict(nc=22, dilation=(False, True, True), audio="vgg", in_plane=1, H=224, W=224, frames=96,
+                     max_views=512),
+            workload="configs[1]: ResNet-50 + VGGish CAVP fwd+bwd bs32/GPU, synthetic VPO-SS shapes (22 cls, dilation "
+                     "FTT), fp32",
+            flops=298.67e9),  # reference-equivalent fwd+bwd conv+GEMM FLOPs per image
+    2: dict(cfg=dict(nc=71, dilation=(False, False, False), audio="vgg", in_plane=1, H=224, W=224, frames=96,
+                     max_views=512),
+            workload="configs[2]: AVSBench-Semantics config (71 cls, dilation FFF) bf16 training loop, bs32/GPU, NCCL "
+                     "grad allreduce",
+            flops=169.20e9),
+}
+CFG = dict(CONFIGS[1]["cfg"])
+WORKLOAD = CONFIGS[1]["workload"]
 METRIC = "AVS train-step images/sec @224^2 bs32/GPU"
-FLOPS_PER_IMAGE = 298.67e9  # reference-equivalent fwd+bwd conv+GEMM FLOPs per image for this config
+FLOPS_PER_IMAGE = CONFIGS[1]["flops"]
+
+
+def select_config(idx):
+    global WORKLOAD, FLOPS_PER_IMAGE
+    CFG.clear()
+    CFG.update(CONFIGS[idx]["cfg"])
+    WORKLOAD = CONFIGS[idx]["workload"]
+    FLOPS_PER_IMAGE = CONFIGS[idx]["flops"]
 
 
 def synthetic_batch(B, seed):
@@ -462,10 +483,14 @@ def run_ours(args):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_res, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32" if args.prec == 2 else "tf32", "data": "synthetic",
+                "vs_baseline": None, "dtype": {1: "tf32", 2: "f32", 3: "bf16"}[args.prec], "data": "synthetic",
                 "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world,
-                           "parallelism": f"dp{world}", "precision": "fp32 I/O, 3xTF32 tcgen05 products + fp32 promotion"
-                           if args.prec == 2 else "fp32 I/O, TF32 tcgen05 products",
+                           "parallelism": f"dp{world}",
+                           "precision": {2: "fp32 I/O, 3xTF32 tcgen05 products + fp32 promotion",
+                                         1: "fp32 I/O, TF32 tcgen05 products",
+                                         3: "bf16 operands (tcgen05 kind::f16, fp32 accumulate in TMEM) for forward / "
+                                            "dgrad GEMMs, TF32 weight gradients, fp32 activations / BN statistics / "
+                                            "LayerNorm / losses; stems and classifier fp32-grade"}[args.prec],
                            "l2": "working set per step (>10 GB of activations) far exceeds the 126 MB L2; no flush needed",
                            "bn": "local (per-rank) BatchNorm statistics"},
                 "clocks": clocks,
@@ -488,7 +513,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="images per GPU")
-    ap.add_argument("--prec", type=int, default=2, help="2 = fp32-parity (3xTF32 + promotion), 1 = plain TF32")
+    ap.add_argument("--prec", type=int, default=2, choices=[1, 2, 3],
+                    help="2 = fp32-parity (3xTF32 + promotion, the headline), 1 = plain TF32, 3 = bf16 operands")
+    ap.add_argument("--config", type=int, default=None, choices=[1, 2],
+                    help="BASELINE.json configs index: 1 = VPO-SS fp32 (default), 2 = AVSS 71 cls FFF (default for --prec 3)")
     ap.add_argument("--cpu-batch", type=int, default=None,
                     help="images per CPU reference step (default: 32 for --impl reference, 8 for the inline cpu_baseline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -496,6 +524,7 @@ def main():
                     help="skip the stock-PyTorch-on-this-GPU arm (gpu_stock_baseline) and the TF32 peak measurement")
     ap.add_argument("--dump-profile", default=None, help="write the per-launch CUDA-event profile of one step here")
     args = ap.parse_args()
+    select_config(args.config if args.config is not None else (2 if args.prec == 3 else 1))
     if args.impl == "reference":
         run_reference(args)
     else:

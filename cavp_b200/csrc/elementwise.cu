@@ -1,6 +1,7 @@
 // HBM-bound kernels around the tensor-core tiles: layout changes, BatchNorm (train/eval, fwd/bwd), pooling,
 // bilinear resampling.  All tensors are NHWC fp32 with an explicit pixel stride (ld) so channel slices work in place.
 // Each extern "C" entry cites the reference op it stands in for (paths relative to the reference repo).
+#include <cuda_bf16.h>
 #include "common.cuh"
 #include "../../include/cavp_b200.h"
 
@@ -73,6 +74,7 @@ struct TsTensor {
 };
 static_assert(sizeof(TsTensor) == 72, "table row layout");
 
+template <bool BF16>
 __global__ void __launch_bounds__(256)
 transpose_split_multi_kernel(const TsTensor* __restrict__ table, const int2* __restrict__ work, int nwork) {
   __shared__ float tile[32][33];
@@ -94,10 +96,14 @@ transpose_split_multi_kernel(const TsTensor* __restrict__ table, const int2* __r
       const int cc = c0 + j, r = r0 + tx;
       if (cc < t.cols && r < t.rows) {
         const float v = tile[tx][j];
-        const float h = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
         const long long o = z * t.dst_bs + cc * t.dst_ld + r;
-        t.hi[o] = h;
-        t.lo[o] = __uint_as_float((__float_as_uint(v - h) + 0x1000u) & 0xFFFFE000u);
+        if (BF16) {  // `hi` is a bf16 destination (the bf16 dgrad operand of the configs[2] path)
+          reinterpret_cast<__nv_bfloat16*>(t.hi)[o] = __float2bfloat16_rn(v);
+        } else {
+          const float h = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
+          t.hi[o] = h;
+          t.lo[o] = __uint_as_float((__float_as_uint(v - h) + 0x1000u) & 0xFFFFE000u);
+        }
       }
     }
   }
@@ -663,13 +669,17 @@ extern "C" int cavp_transpose_split(const float* src, float* hi, float* lo, int 
   transpose_kernel<<<grid, block, 0, ST(stream)>>>(src, hi, lo, rows, cols, src_ld, dst_ld, src_bs, dst_bs);
   CAVP_LAUNCH_CHECK();
 }
-extern "C" int cavp_transpose_split_multi(const void* table, const int* work, int nwork, void* stream) {
+extern "C" int cavp_transpose_split_multi(const void* table, const int* work, int nwork, int bf16, void* stream) {
   if (!table || !work) return CAVP_ERR_NULL;
   if (nwork <= 0) return 0;
   if ((reinterpret_cast<uintptr_t>(table) & 7) || (reinterpret_cast<uintptr_t>(work) & 7)) return CAVP_ERR_ALIGN;
   const int grid = nwork < NUM_SMS * 16 ? nwork : NUM_SMS * 16;
-  transpose_split_multi_kernel<<<grid, 256, 0, ST(stream)>>>(static_cast<const TsTensor*>(table),
-                                                             reinterpret_cast<const int2*>(work), nwork);
+  if (bf16)
+    transpose_split_multi_kernel<true><<<grid, 256, 0, ST(stream)>>>(static_cast<const TsTensor*>(table),
+                                                                     reinterpret_cast<const int2*>(work), nwork);
+  else
+    transpose_split_multi_kernel<false><<<grid, 256, 0, ST(stream)>>>(static_cast<const TsTensor*>(table),
+                                                                      reinterpret_cast<const int2*>(work), nwork);
   CAVP_LAUNCH_CHECK();
 }
 extern "C" int cavp_add_inplace(float* dst, const float* src, long long n, float alpha, void* stream) {

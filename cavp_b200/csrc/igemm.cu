@@ -2,10 +2,10 @@
 #include <cstring>
 #include <cstdlib>
 #include "igemm.cuh"
-#include "igemm_ts.cuh"
 #include "igemm_ws.cuh"
 #include "igemm_ws2.cuh"
 #include "igemm_wgrad2.cuh"
+#include "igemm_bf16.cuh"
 #include "../../include/cavp_b200.h"
 
 namespace cavp {
@@ -66,23 +66,6 @@ template <int BN, int PREC, int MODE, bool BTMA>
 static int launch_igemm(const IgemmParams& p, const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, cudaStream_t st) {
   using Cfg = TileCfg<BN, PREC>;
   auto kern = igemm_kernel<BN, PREC, MODE, BTMA>;
-  static bool configured_dev[MAX_DEVICES] = {};
-  bool& configured = configured_dev[current_device()];
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    configured = true;
-  }
-  const int m_tiles = (p.M + BM - 1) / BM;
-  dim3 grid(static_cast<unsigned>(m_tiles * p.n_tiles), static_cast<unsigned>(p.splits), 1);
-  kern<<<grid, CTA_THREADS, Cfg::SMEM_BYTES, st>>>(p, tm_hi, tm_lo);
-  return static_cast<int>(cudaGetLastError());
-}
-
-template <int BN, int PREC>
-static int launch_igemm_ts(const IgemmParams& p, const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, cudaStream_t st) {
-  using Cfg = TsCfg<BN, PREC>;
-  auto kern = igemm_ts_kernel<BN, PREC>;
   static bool configured_dev[MAX_DEVICES] = {};
   bool& configured = configured_dev[current_device()];
   if (!configured) {
@@ -162,6 +145,55 @@ static int launch_wgrad2(const IgemmParams& p, const CUtensorMap& tm_hi, const C
   return static_cast<int>(cudaGetLastError());
 }
 
+// [rows][ld] bf16 matrix, box = 64 (K) x bn rows, 128-byte swizzle, out-of-bounds elements read as zero
+static int make_weight_tmap_bf16(CUtensorMap* tm, const void* w, int rows, int K, int ld, int bn) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return CAVP_ERR_ARG;
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK16), static_cast<cuuint32_t>(bn)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 1000 + static_cast<int>(r);
+}
+
+// bf16 CTA-pair kernel: persistent over (256-row pair tile, n tile, split) work items, one cluster of 2 per TPC
+template <int BN>
+static int launch_igemm_bf16(IgemmParams& p, const void* w_bf16, cudaStream_t st) {
+  using Cfg = Bf16Cfg<BN>;
+  auto kern = igemm_bf16_pair_kernel<BN>;
+  static int max_pairs_dev[MAX_DEVICES] = {};
+  int& max_pairs = max_pairs_dev[current_device()];
+  if (max_pairs == 0) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(148, 1, 1);
+    cfg.blockDim = dim3(WS_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    int n = 0;
+    e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+    if (e != cudaSuccess || n < 1) {
+      cudaGetLastError();
+      n = 74;
+    }
+    max_pairs = n;
+  }
+  p.n_tiles = (p.Ncols + BN - 1) / BN;
+  CUtensorMap tm;
+  memset(&tm, 0, sizeof(tm));
+  int rc = make_weight_tmap_bf16(&tm, w_bf16, p.Ncols, p.K, p.ldw, BN / 2);
+  if (rc) return rc;
+  const int m_tiles = (p.M + BM - 1) / BM;
+  const int m_pairs = (m_tiles + 1) / 2;
+  const int total_work = m_pairs * p.n_tiles * p.splits;
+  const int pairs = total_work < max_pairs ? total_work : max_pairs;
+  kern<<<2 * pairs, WS_THREADS, Cfg::SMEM_BYTES, st>>>(p, tm, total_work, m_pairs);
+  return static_cast<int>(cudaGetLastError());
+}
+
 // b_lo_off > 0: the B operand is pre-split ([hi | lo], lo at w + b_lo_off) and is fetched by TMA
 template <int MODE>
 static int dispatch(IgemmParams& p, int prec, long long b_lo_off, cudaStream_t st) {
@@ -211,12 +243,6 @@ static int dispatch(IgemmParams& p, int prec, long long b_lo_off, cudaStream_t s
         if (prec == 2)
           return bn == 128 ? launch_igemm_ws<128, 2>(p, tm_hi, tm_lo, st) : launch_igemm_ws<64, 2>(p, tm_hi, tm_lo, st);
         return bn == 128 ? launch_igemm_ws<128, 1>(p, tm_hi, tm_lo, st) : launch_igemm_ws<64, 1>(p, tm_hi, tm_lo, st);
-      }
-      static const bool use_ss = getenv("CAVP_IGEMM_TS") == nullptr;  // default: A operand via shared memory (faster); CAVP_IGEMM_TS=1 selects the A-in-TMEM variant
-      if (!use_ss) {
-        if (prec == 2)
-          return bn == 128 ? launch_igemm_ts<128, 2>(p, tm_hi, tm_lo, st) : launch_igemm_ts<64, 2>(p, tm_hi, tm_lo, st);
-        return bn == 128 ? launch_igemm_ts<128, 1>(p, tm_hi, tm_lo, st) : launch_igemm_ts<64, 1>(p, tm_hi, tm_lo, st);
       }
       if (prec == 2)
         return bn == 128 ? launch_igemm<128, 2, MODE, true>(p, tm_hi, tm_lo, st)
@@ -290,15 +316,43 @@ static void fill_divs(IgemmParams& p) {
 
 using namespace cavp;
 
+static int igemm_row_impl(const float* x, const float* w, const void* w_bf16, float* y, float* y_pre,
+                          const float* scale, const float* shift, const float* res, float* stats, int nimg, int hs,
+                          int ws, int c, int ldx, int ho, int wo, int r, int s, int stride, int pad, int dil, int dgrad,
+                          int ncols, int ldw, int ldy, int ldr, int res_mod, int res_div, int ldstat, int act,
+                          float slope, int splits, int prec, long long b_lo_off, void* stream);
+
 extern "C" int cavp_igemm(const float* x, const float* w, float* y, float* y_pre, const float* scale,
                           const float* shift, const float* res, float* stats, int nimg, int hs, int ws, int c, int ldx,
                           int ho, int wo, int r, int s, int stride, int pad, int dil, int dgrad, int ncols, int ldw,
                           int ldy, int ldr, int res_mod, int res_div, int ldstat, int act, float slope, int splits,
                           int prec, long long b_lo_off, void* stream) {
+  if (prec != 1 && prec != 2) return CAVP_ERR_ARG;
+  return igemm_row_impl(x, w, nullptr, y, y_pre, scale, shift, res, stats, nimg, hs, ws, c, ldx, ho, wo, r, s, stride,
+                        pad, dil, dgrad, ncols, ldw, ldy, ldr, res_mod, res_div, ldstat, act, slope, splits, prec,
+                        b_lo_off, stream);
+}
+
+// bf16-operand GEMM (BASELINE.json configs[2]): `w_bf16` is the bf16 copy of the K-major weight operand ([ncols][ldw]);
+// `w` / `b_lo_off` are the fp32 operand used when the shape is outside the bf16 kernel's envelope (plain TF32 then)
+extern "C" int cavp_igemm_bf16(const float* x, const float* w, const void* w_bf16, float* y, float* y_pre,
+                               const float* scale, const float* shift, const float* res, float* stats, int nimg, int hs,
+                               int ws, int c, int ldx, int ho, int wo, int r, int s, int stride, int pad, int dil,
+                               int dgrad, int ncols, int ldw, int ldy, int ldr, int res_mod, int res_div, int ldstat,
+                               int act, float slope, int splits, long long b_lo_off, void* stream) {
+  return igemm_row_impl(x, w, w_bf16, y, y_pre, scale, shift, res, stats, nimg, hs, ws, c, ldx, ho, wo, r, s, stride,
+                        pad, dil, dgrad, ncols, ldw, ldy, ldr, res_mod, res_div, ldstat, act, slope, splits, 1, b_lo_off,
+                        stream);
+}
+
+static int igemm_row_impl(const float* x, const float* w, const void* w_bf16, float* y, float* y_pre,
+                          const float* scale, const float* shift, const float* res, float* stats, int nimg, int hs,
+                          int ws, int c, int ldx, int ho, int wo, int r, int s, int stride, int pad, int dil, int dgrad,
+                          int ncols, int ldw, int ldy, int ldr, int res_mod, int res_div, int ldstat, int act,
+                          float slope, int splits, int prec, long long b_lo_off, void* stream) {
   if (!x || !w || !y) return CAVP_ERR_NULL;
   if ((c & 3) || (ldx & 3) || (ldw & 3) || c <= 0 || ncols <= 0) return CAVP_ERR_ALIGN;
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 15)) return CAVP_ERR_ALIGN;
-  if (prec != 1 && prec != 2) return CAVP_ERR_ARG;
   if (stride < 1 || dil < 1 || r < 1 || s < 1) return CAVP_ERR_ARG;
   const long long M = static_cast<long long>(nimg) * ho * wo;
   if (M <= 0 || M >= (1ll << 31) || static_cast<long long>(nimg) * hs * ws * ldx >= (1ll << 31)) return CAVP_ERR_ARG;
@@ -309,7 +363,11 @@ extern "C" int cavp_igemm(const float* x, const float* w, float* y, float* y_pre
   p.M = static_cast<int>(M); p.Ncols = ncols; p.K = r * s * c; p.ldw = ldw; p.ldy = ldy; p.ldr = ldr;
   p.res_mod = res_mod; p.res_div = res_div; p.ldstat = ldstat; p.act = act; p.slope = slope;
   p.red_len = p.K;
-  p.num_kb = (p.K + BK - 1) / BK;
+  // bf16 kernel envelope: 8-element chunks never straddle a filter tap, TMA strides are multiples of 16 bytes
+  const bool use_bf16 = w_bf16 != nullptr && (c & 7) == 0 && (ldw & 7) == 0 &&
+                        (reinterpret_cast<uintptr_t>(w_bf16) & 15) == 0;
+  const int bk = use_bf16 ? BK16 : BK;
+  p.num_kb = (p.K + bk - 1) / bk;
   // splits < 0: deterministic split-K - y holds |splits| slabs of M*ldy floats, split i stores its raw partial product
   // in slab i (no atomics, no pre-zeroing); the caller sums the slabs in a fixed order
   const bool slabs = splits < -1;
@@ -320,6 +378,14 @@ extern "C" int cavp_igemm(const float* x, const float* w, float* y, float* y_pre
   if (p.splits > 1 && (y_pre || scale || shift || res || stats || act != ACT_NONE)) return CAVP_ERR_ARG;
   fill_divs(p);
   if (b_lo_off > 0 && ((b_lo_off & 3) || (reinterpret_cast<uintptr_t>(w) & 15))) return CAVP_ERR_ALIGN;
+  if (use_bf16) {
+    // 256-column pair tiles where they pad N no more than 128-column tiles do (N = 256, 512, 1024, 2048 ...)
+    const int pad128 = (ncols + 127) / 128 * 128, pad256 = (ncols + 255) / 256 * 256;
+    static const char* bn_env = getenv("CAVP_BF16_BN");
+    const bool bn256 = bn_env ? bn_env[0] == '2' : pad256 == pad128;
+    return bn256 ? launch_igemm_bf16<256>(p, w_bf16, static_cast<cudaStream_t>(stream))
+                 : launch_igemm_bf16<128>(p, w_bf16, static_cast<cudaStream_t>(stream));
+  }
   return dispatch<MODE_ROW>(p, prec, b_lo_off, static_cast<cudaStream_t>(stream));
 }
 

@@ -7,6 +7,7 @@
 // a block owns 16 K-element chunks, so the 50 M-element VGG FC weight and a 64-element BN bias share the grid evenly.
 // HBM-bound: SGD reads p, g, buf and writes p, buf (20 B / element); Adam reads p, g, m, v, writes p, m, v (28 B).
 #include <cstdint>
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include "../../include/cavp_b200.h"
 #include "common.cuh"
@@ -153,6 +154,30 @@ copy_multi_kernel(const CopyTensor* __restrict__ table, const int2* __restrict__
   }
 }
 
+// fp32 -> bf16 copies of every weight operand in one launch (bf16 path of BASELINE.json configs[2]); rows {src, dst, n}
+__global__ void __launch_bounds__(OPT_THREADS)
+cvt_bf16_multi_kernel(const CopyTensor* __restrict__ table, const int2* __restrict__ work, int nwork) {
+  for (int wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
+    const int2 w = work[wi];
+    const CopyTensor t = table[w.x];
+    const long long off = static_cast<long long>(w.y) * OPT_CHUNK;
+    const int n = static_cast<int>(t.n - off < OPT_CHUNK ? t.n - off : OPT_CHUNK);
+    const float* src = t.src + off;
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(t.dst) + off;
+    const bool al = ((reinterpret_cast<uintptr_t>(src) & 15) | (reinterpret_cast<uintptr_t>(dst) & 7)) == 0;
+    const int n4 = al ? (n >> 2) : 0;
+    for (int i = threadIdx.x; i < n4; i += OPT_THREADS) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+      __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+      uint2 o;
+      o.x = *reinterpret_cast<uint32_t*>(&a);
+      o.y = *reinterpret_cast<uint32_t*>(&b);
+      reinterpret_cast<uint2*>(dst)[i] = o;
+    }
+    for (int i = n4 * 4 + threadIdx.x; i < n; i += OPT_THREADS) dst[i] = __float2bfloat16_rn(src[i]);
+  }
+}
+
 static int opt_grid(int nwork) {
   const int cap = NUM_SMS * 8;
   return nwork < cap ? (nwork < 1 ? 1 : nwork) : cap;
@@ -202,6 +227,15 @@ extern "C" int cavp_copy_multi(const void* table, const int* work, int nwork, vo
   if (nwork <= 0) return 0;
   if ((reinterpret_cast<uintptr_t>(table) & 7) || (reinterpret_cast<uintptr_t>(work) & 7)) return CAVP_ERR_ALIGN;
   copy_multi_kernel<<<opt_grid(nwork), OPT_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const CopyTensor*>(table), reinterpret_cast<const int2*>(work), nwork);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int cavp_cvt_bf16_multi(const void* table, const int* work, int nwork, void* stream) {
+  if (!table || !work) return CAVP_ERR_NULL;
+  if (nwork <= 0) return 0;
+  if ((reinterpret_cast<uintptr_t>(table) & 7) || (reinterpret_cast<uintptr_t>(work) & 7)) return CAVP_ERR_ALIGN;
+  cvt_bf16_multi_kernel<<<opt_grid(nwork), OPT_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const CopyTensor*>(table), reinterpret_cast<const int2*>(work), nwork);
   return static_cast<int>(cudaGetLastError());
 }

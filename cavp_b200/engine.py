@@ -115,24 +115,34 @@ class WeightRef:
         if self._split is None:
             cache = self.g.wcache
             if cache is not None and self.kind in ("linear", "cl") and self.cout_eff == self.cout:
-                hit = cache.operand(self.param)
-                if hit is not None:
-                    self._split, self._lo_off = hit
-                    return self._split, self._lo_off
-            self._split = self._presplit(self.wk)
-            self._lo_off = self.wk.numel()
-        return self._split, self._lo_off
+                if cache.bf16:
+                    hit = cache.operand_bf16(self.param)
+                    if hit is not None:  # (fp32 operand for the ABI's fallback slot, no split, bf16 copy)
+                        self._split = (self.wk, 0, hit)
+                        return self._split
+                else:
+                    hit = cache.operand(self.param)
+                    if hit is not None:
+                        self._split = hit
+                        return self._split
+            self._split = (self._presplit(self.wk), self.wk.numel())
+        return self._split
 
     def operand_t(self):
         """[hi | lo] split of the transposed operand [Cin][taps][Cout_eff] for the data-gradient GEMM (one kernel)."""
         if self._wt_split is None:
             cache = self.g.wcache
             if cache is not None and self.kind in ("linear", "cl") and self.cout_eff == self.cout:
-                hit = cache.operand_t(self.param)
-                if hit is not None:
-                    self._wt_split = hit[0]
-                    self._wt_lo_off = hit[1]
-                    return self._wt_split, self._wt_lo_off
+                if cache.bf16:
+                    hit = cache.operand_t_bf16(self.param)
+                    if hit is not None:
+                        return (self.wk, 0, hit)
+                else:
+                    hit = cache.operand_t(self.param)
+                    if hit is not None:
+                        self._wt_split = hit[0]
+                        self._wt_lo_off = hit[1]
+                        return self._wt_split, self._wt_lo_off
             taps = self.r * self.s
             sp = self.g.empty(2, self.cin, taps * self.cout_eff)
             self.g.call("cavp_transpose_split", self.wk.data_ptr(), sp[0].data_ptr(), sp[1].data_ptr(), self.cout_eff,
@@ -171,9 +181,13 @@ class WeightSplitCache:
     Cin % 4 == 0 and Linear weights), refreshed by ONE kernel launch per step (cavp_split_tf32_multi).  The buffers and
     the device table are built once; they are rebuilt if a parameter's storage moves."""
 
-    def __init__(self, params, device):
+    def __init__(self, params, device, bf16=False):
         self.params = list(params)
         self.device = device
+        self.bf16 = bf16  # prec 3: bf16 copies (K-major and transposed) instead of the TF32 hi | lo splits
+        if bf16:
+            self._init_bf16()
+            return
         self.ptrs = [p.data_ptr() for p in self.params]
         total = sum(p.numel() for p in self.params)
         self.buf = torch.empty(2, total, device=device, dtype=torch.float32)
@@ -217,7 +231,7 @@ class WeightSplitCache:
         if self._t is None:
             self._build_transposed()
         g.call("cavp_transpose_split_multi", self._t["table"].data_ptr(), self._t["work"].data_ptr(),
-               self._t["work"].shape[0])
+               self._t["work"].shape[0], 0)
 
     def operand_t(self, param):
         """(hi tensor [Cin, taps*Cout], lo offset in elements) or None"""
@@ -226,12 +240,55 @@ class WeightSplitCache:
         v = self._t["views"].get(id(param))
         return None if v is None else (v, self.lo_off)
 
+    def _init_bf16(self):
+        """bf16 operands of the configs[2] path: [cout][K] copies for forward and [Cin][taps][Cout] transposes for the
+        data-gradient GEMMs; each refreshed by one launch per step (cavp_cvt_bf16_multi / cavp_transpose_split_multi)."""
+        self.ptrs = [p.data_ptr() for p in self.params]
+        total = sum((p.numel() + 7) // 8 * 8 for p in self.params)  # every operand starts 16-byte aligned
+        self.buf = torch.empty(2, total, device=self.device, dtype=torch.bfloat16)
+        chunk = _C.query("cavp_opt_chunk_elems")
+        self.views, self.t_views, rows, trows, work, twork, off = {}, {}, [], [], [], [], 0
+        for i, p in enumerate(self.params):
+            n = p.numel()
+            cout, cin = p.shape[0], p.shape[1]
+            taps = n // (cout * cin)
+            fw, tr = self.buf[0, off:off + n], self.buf[1, off:off + n]
+            self.views[id(p)] = fw.view(cout, taps * cin)
+            self.t_views[id(p)] = tr.view(cin, taps * cout)
+            rows.append((p.data_ptr(), fw.data_ptr(), n))
+            work.extend((i, c) for c in range((n + chunk - 1) // chunk))
+            tiles_c, tiles_r = (cin + 31) // 32, (cout + 31) // 32
+            trows.append((p.data_ptr(), tr.data_ptr(), 0, cout | (cin << 32), taps * cin, taps * cout, cin, cout,
+                          tiles_c | (tiles_r << 32)))
+            twork.extend((i, t) for t in range(taps * tiles_c * tiles_r))
+            off += (n + 7) // 8 * 8
+        dev = self.device
+        self.table = torch.tensor(rows, dtype=torch.int64).to(dev)
+        self.work = torch.tensor(work, dtype=torch.int32).reshape(-1, 2).to(dev)
+        self.t_table = torch.tensor(trows, dtype=torch.int64).to(dev)
+        self.t_work = torch.tensor(twork, dtype=torch.int32).reshape(-1, 2).to(dev)
+
+    def refresh_bf16(self, g, train):
+        g.call("cavp_cvt_bf16_multi", self.table.data_ptr(), self.work.data_ptr(), self.work.shape[0])
+        if train:
+            g.call("cavp_transpose_split_multi", self.t_table.data_ptr(), self.t_work.data_ptr(), self.t_work.shape[0], 1)
+
+    def operand_bf16(self, param):
+        return self.views.get(id(param))
+
+    def operand_t_bf16(self, param):
+        return self.t_views.get(id(param))
+
     @staticmethod
-    def eligible(model):
+    def eligible(model, bf16=False):
         out = []
         for mod in model.modules():
             w = getattr(mod, "weight", None)
-            if isinstance(mod, torch.nn.Linear) and w is not None and w.is_contiguous():
+            if w is None or not isinstance(mod, (torch.nn.Linear, torch.nn.Conv2d)):
+                continue
+            if bf16 and (w.shape[0] % 8 or w.shape[1] % 8):
+                continue  # 8-element bf16 chunks / 16-byte TMA strides; such layers run the TF32 kernels
+            if isinstance(mod, torch.nn.Linear) and w.is_contiguous():
                 out.append(w)
             elif isinstance(mod, torch.nn.Conv2d) and w.shape[1] % 4 == 0 and w.permute(0, 2, 3, 1).is_contiguous():
                 out.append(w)
@@ -255,7 +312,12 @@ class Graph:
         # grad_sink: a cavp_b200.parallel.FlatGradBuffer - weight-gradient kernels write straight into its views
         self.grad_sink = grad_sink
         self.callbacks = {}  # name -> callable, fired by the matching tape marker during backward()
-        self.prec = prec
+        self.prec = prec  # 2 = fp32 parity (3xTF32 + promotion), 1 = plain TF32, 3 = bf16 operands (configs[2])
+        # bf16 mode: forward / dgrad GEMMs outside the bf16 kernel's envelope (3/4-channel stems, the padded classifier,
+        # the InfoNCE similarity) keep fp32-grade products - a TF32-rounded stem would be amplified ~1000x by the
+        # batch-stat BN chain; weight gradients run plain TF32 (one MMA per product)
+        self.prec_tf = 2 if prec == 3 else prec
+        self.prec_wg = 1 if prec == 3 else prec
         self.train = train
         self.tape = []
         self.param_grads = {}  # id(param) -> gradient tensor
@@ -271,16 +333,20 @@ class Graph:
 
     def use_weight_cache(self, model):
         """Refresh (one launch) the persistent TF32 splits of the model's weight operands for this step."""
+        bf16 = self.prec == 3
         cache = model.__dict__.get("_cavp_wsplit")
-        if cache is None or cache.device != self.device or not cache.valid():
-            params = WeightSplitCache.eligible(model)
+        if cache is None or cache.device != self.device or cache.bf16 != bf16 or not cache.valid():
+            params = WeightSplitCache.eligible(model, bf16)
             if not params:
                 return
-            cache = WeightSplitCache(params, self.device)
+            cache = WeightSplitCache(params, self.device, bf16)
             model.__dict__["_cavp_wsplit"] = cache
-        self.call("cavp_split_tf32_multi", cache.table.data_ptr(), cache.work.data_ptr(), cache.work.shape[0])
-        if self.train:
-            cache.refresh_transposed(self)  # the dgrad operands of every layer, one launch
+        if bf16:
+            cache.refresh_bf16(self, self.train)
+        else:
+            self.call("cavp_split_tf32_multi", cache.table.data_ptr(), cache.work.data_ptr(), cache.work.shape[0])
+            if self.train:
+                cache.refresh_transposed(self)  # the dgrad operands of every layer, one launch
         self.wcache = cache
 
     # ------------------------------------------------------------------ small helpers
@@ -412,15 +478,24 @@ class Graph:
         """geom = (ho, wo, r, s, stride, pad, dil).  x: A-operand source Act; y: output Act (rows = x.n*ho*wo)."""
         ho, wo, r, s, stride, pad, dil = geom
         hs, ws = (x.h, x.w) if src_hw is None else src_hw
-        b_lo_off = 0
-        if isinstance(wk, tuple):  # pre-split weight operand -> TMA path
-            wk, b_lo_off = wk
+        b_lo_off, w16 = 0, None
+        if isinstance(wk, tuple):  # pre-split weight operand -> TMA path; (fp32, 0, bf16 copy) -> bf16 kernel
+            if len(wk) == 3:
+                wk, b_lo_off, w16 = wk
+            else:
+                wk, b_lo_off = wk
         self.work(flops=2.0 * x.n * ho * wo * ncols * r * s * x.c,
                   tag=f"{'dgrad' if dgrad else 'fwd'} M{x.n * ho * wo} N{ncols} K{r * s * x.c} k{r} s{stride} d{dil} splits{splits}")
+        if w16 is not None:
+            self.call("cavp_igemm_bf16", x.ptr, wk.data_ptr(), w16.data_ptr(), y.ptr, 0 if y_pre is None else y_pre.ptr,
+                      _C.ptr(scale), _C.ptr(shift), 0 if res is None else res.ptr, stats_ptr, x.n, hs, ws, x.c, x.ld, ho,
+                      wo, r, s, stride, pad, dil, dgrad, ncols, ldw, y.ld, 0 if res is None else res.ld, res_mod,
+                      res_div, ldstat, act, LEAKY_SLOPE, splits, b_lo_off)
+            return
         self.call("cavp_igemm", x.ptr, wk.data_ptr(), y.ptr, 0 if y_pre is None else y_pre.ptr, _C.ptr(scale),
                   _C.ptr(shift), 0 if res is None else res.ptr, stats_ptr, x.n, hs, ws, x.c, x.ld, ho, wo, r, s, stride,
                   pad, dil, dgrad, ncols, ldw, y.ld, 0 if res is None else res.ld, res_mod, res_div, ldstat, act,
-                  LEAKY_SLOPE, splits, self.prec, b_lo_off)
+                  LEAKY_SLOPE, splits, self.prec_tf, b_lo_off)
 
     @staticmethod
     def fwd_splits(M, ncols, K):
@@ -597,12 +672,12 @@ class Graph:
                         self.work(flops=2.0 * M * co * K,
                                   tag=f"wgrad(tma) P{M} Cout{co} K{K} k{r} s{stride} d{dil} splits{wsplits}")
                         self.call("cavp_igemm_wgrad_tma", gsp[0].data_ptr(), gsp[0].numel(), x.ptr, dwk.data_ptr(), x.n,
-                                  x.h, x.w, x.c, x.ld, ho, wo, r, s, stride, pad, dil, co, wsplits, self.prec)
+                                  x.h, x.w, x.c, x.ld, ho, wo, r, s, stride, pad, dil, co, wsplits, self.prec_wg)
                     else:
                         self.work(flops=2.0 * M * co * K,
                                   tag=f"wgrad P{M} Cout{co} K{K} k{r} s{stride} d{dil} splits{wsplits}")
                         self.call("cavp_igemm_wgrad", g.ptr, x.ptr, dwk.data_ptr(), x.n, x.h, x.w, x.c, x.ld, ho, wo, r,
-                                  s, stride, pad, dil, co, g.ld, wsplits, self.prec)
+                                  s, stride, pad, dil, co, g.ld, wsplits, self.prec_wg)
                     wr.deliver_grad(dwk)
                 if x.needs_grad:
                     wt = wr.operand_t()

@@ -96,7 +96,7 @@ class InfoNCE:
         if wsplits > 1:
             g.call("cavp_zero", d2.data_ptr(), d2.numel() * 4)
         g.call("cavp_igemm_wgrad", G.data_ptr(), self.anchors.data_ptr(), d2.data_ptr(), A, 1, 1, C, C, 1, 1, 1, 1, 1, 0,
-               1, A4, A4, wsplits, g.prec)
+               1, A4, A4, wsplits, g.prec_tf)
         g.call("cavp_add_inplace", d1.data_ptr(), d2.data_ptr(), A * C, 1.0)
         row = 0
         for (base, ld, pix, _), (gbase, gld) in zip(self.sources, targets):

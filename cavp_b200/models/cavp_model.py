@@ -480,7 +480,10 @@ class CAVP(nn.Module):
         self.ignore_index = ignore_index
         self.in_plane = in_plane
         self.audio_kind = "vgg" if args.audio_backbone == "vgg" else "resnet18"
-        self.prec = int(getattr(args, "cavp_prec", 2))  # 2 = fp32-parity (3xTF32 + promotion), 1 = plain TF32
+        # 2 = fp32-parity (3xTF32 + promotion), 1 = plain TF32, 3 = bf16 operands / fp32 accumulate (BASELINE configs[2])
+        self.prec = int(getattr(args, "cavp_prec", 2))
+        if self.prec not in (1, 2, 3):
+            raise ValueError("cavp_prec must be 1 (TF32), 2 (fp32 parity) or 3 (bf16 operands)")
         self._to_channels_last()
 
     # ---- parameter storage: conv weights live in OHWI (channels_last) so the kernels read them without copies

@@ -51,6 +51,15 @@ int cavp_split_tf32(const float* w, float* hi, float* lo, long long n, void* str
 /* the same split for every weight operand of a model in ONE launch: table = device array of 32-byte rows {const float*
  * src; float* hi; float* lo; long long n}, work = (row, chunk) int pairs with chunk = cavp_opt_chunk_elems() elements */
 int cavp_split_tf32_multi(const void* table, const int* work, int nwork, void* stream);
+/* cavp_igemm with bf16 operands (BASELINE.json configs[2] "bf16 training loop"; the reference has no bf16 path):
+ * tcgen05.mma.kind::f16, bf16 A/B, fp32 accumulation in TMEM, fp32 activations / epilogue / statistics.  w_bf16 =
+ * bf16 copy of the K-major weight operand [ncols][ldw]; the fp32 activations are converted by the producer warps.
+ * Shapes outside the kernel's envelope (c % 8, ldw % 8) run the TF32 kernels on `w` / `b_lo_off` instead. */
+int cavp_igemm_bf16(const float* x, const float* w, const void* w_bf16, float* y, float* y_pre, const float* scale,
+                    const float* shift, const float* res, float* stats, int nimg, int hs, int ws, int c, int ldx, int ho,
+                    int wo, int r, int s, int stride, int pad, int dil, int dgrad, int ncols, int ldw, int ldy, int ldr,
+                    int res_mod, int res_div, int ldstat, int act, float slope, int splits, long long b_lo_off,
+                    void* stream);
 /* cavp_igemm_wgrad: dw[cout][r*s*c] (+)= dy[P][cout]^T * im2col(x)[P][r*s*c]   (weight gradient; P = nimg*ho*wo).
  *   splits > 1 accumulates into a PRE-ZEROED dw. */
 int cavp_igemm_wgrad(const float* dy, const float* x, float* dw, int nimg, int hs, int ws, int c, int ldx, int ho,
@@ -81,7 +90,8 @@ int cavp_transpose_split(const float* src, float* hi, float* lo, int rows, int c
 /* cavp_transpose_split for every dgrad weight operand of a model in ONE launch: table = device array of 72-byte rows
  * {const float* src; float* hi; float* lo; int rows, cols; long long src_ld, dst_ld, src_bs, dst_bs; int tiles_c,
  * tiles_r}; work = (row, tile) int pairs, tile enumerating (batch, 32-row tile, 32-column tile). */
-int cavp_transpose_split_multi(const void* table, const int* work, int nwork, void* stream);
+int cavp_transpose_split_multi(const void* table, const int* work, int nwork, int bf16, void* stream);
+/* ^ bf16 != 0: `hi` points to a bf16 destination and receives the rounded transpose (lo unused) */
 int cavp_add_inplace(float* dst, const float* src, long long n, float alpha, void* stream);
 /* dst[i] = src[idx[i]] (fea_a[shuffle_idx], models/cavp_model.py:171) or, accumulate_scatter=1, dst[idx[i]] += src[i] */
 int cavp_gather_rows(const float* src, const long long* idx, float* dst, int nrows, int c, int accumulate_scatter,
@@ -201,6 +211,8 @@ int cavp_adam_multi(const void* table, const int* work, int nwork, double beta1,
  * (row, chunk) work list.  Packs the gradients that were not produced in place into the flat all-reduce buffer
  * (cavp_b200/parallel.py; the reference's DDP reducer copies into its buckets the same way, main_vpo_mono.py:131-141). */
 int cavp_copy_multi(const void* table, const int* work, int nwork, void* stream);
+/* same table format, dst = bf16: the bf16 copies of every weight operand of the model, one launch per step */
+int cavp_cvt_bf16_multi(const void* table, const int* work, int nwork, void* stream);
 
 /* ---- eval epilogue (csrc/metrics.cu) -----------------------------------------------------------
  * Replace torch.max(logits, 1) + 3x torch.histc (utils/eval_utils.py:73-97, MIoU) and argmax -> .cpu().numpy() ->

@@ -1,7 +1,7 @@
 """Import the UNMODIFIED reference (/root/reference) in the build container.
 
 TEST INFRASTRUCTURE ONLY. Used by oracle/make_golden.py to produce tests/golden/*.pt and by
-tests/test_oracle_vs_reference.py (skipped when /root/reference is absent, i.e. on the GPU box).
+tests/test_reference_dropin.py (marked `reference`: skipped when /root/reference is absent, i.e. on the GPU box).
 
 The reference needs three non-invasive shims:
   1. `timm` (pinned timm==0.4.9 in /root/reference/requirements.txt:21, not installed here):
