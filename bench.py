@@ -308,8 +308,21 @@ def run_ours(args):
         # them, and stdout stays the one JSON line.  A level set by the caller wins.
         os.environ.setdefault("NCCL_DEBUG", "INFO")
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        nccl_log = None
+        if "NCCL_DEBUG_FILE" not in os.environ:  # NCCL writes to a per-rank file; it is copied to stderr below
+            nccl_log = f"/tmp/cavp_nccl_rank{rank}_{os.getpid()}.log"
+            os.environ["NCCL_DEBUG_FILE"] = nccl_log
         dist.init_process_group("nccl", device_id=dev)
+        probe = torch.ones(1, device=dev)
+        dist.all_reduce(probe)  # forces communicator creation so that its INIT lines exist before the timed region
+        torch.cuda.synchronize()
+        sys.stderr.write(f"[cavp_b200] rank {rank}: torch.distributed NCCL communicator up, nranks {world} "
+                         f"(all-reduce probe = {int(probe.item())}), NCCL {'.'.join(map(str, torch.cuda.nccl.version()))}\n")
+        if nccl_log and os.path.exists(nccl_log):
+            for ln in open(nccl_log, errors="replace"):
+                if any(k in ln for k in ("nranks", "Init COMPLETE", "NVLS", "Connected", "NCCL version", "Channel 00")):
+                    sys.stderr.write(ln)
+        sys.stderr.flush()
     B = args.batch
     torch.manual_seed(666 + rank)  # main_*.py: seed_it(seed + local_rank), seed 666
     model = CAVP(50, None, num_classes=CFG["nc"], ignore_index=255, audio_backbone_pretrain_path=None,

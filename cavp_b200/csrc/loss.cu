@@ -1,6 +1,7 @@
 // Loss kernels.  Reference: loss/losser.py:60-62 (CrossEntropyLoss(ignore_index=255), mean over valid pixels) and
 // loss/contrastive_aud.py:17-74 (pixel InfoNCE).  Coalesced, vectorised reductions with warp shuffles; every
 // cross-block reduction goes through a partials buffer and a single finishing block, so results are deterministic.
+#include <cstdlib>
 #include "common.cuh"
 #include "../../include/cavp_b200.h"
 
@@ -179,6 +180,123 @@ upsample_ce_bwd_kernel(const float* __restrict__ x, int ldx, int hin, int win, i
   }
 }
 
+// Exact 4x upsampling (the model's case: logits at stride 4 of an input whose sides are multiples of 4): the same
+// gradient, tiled through shared memory.  A block owns an 8 x 8 tile of low-resolution pixels of one image.  The
+// 36 x 36 full-resolution pixels whose footprint touches the tile are visited ONCE per 8-channel chunk: phase B
+// evaluates g = softmax - onehot for (pixel, channel) from the low-resolution tile held in shared memory, phase C
+// gathers the <= 8 x 8 weighted g values of every low-resolution element (weights from lerp_index, so the clamped
+// borders match the forward exactly).  Deterministic (no atomics); ~6 shared-memory operations per (output pixel,
+// channel) instead of 64 x (4 global loads + exp) per low-resolution element.
+constexpr int UCE_T = 8;                  // low-resolution tile side
+constexpr int UCE_R = 4 * UCE_T + 4;      // full-resolution region side (36)
+constexpr int UCE_H = UCE_T + 2;          // low-resolution tile + halo (10)
+constexpr int UCE_CC = 8;                 // channels per chunk
+constexpr int UCE_GS = UCE_CC + 1;        // padded row of the g tile (bank spread)
+constexpr int UCE_SMEM = UCE_R * UCE_R * (4 + 2) + UCE_H * UCE_H * UCE_CC * 4 + UCE_R * UCE_R * UCE_GS * 4;
+
+__global__ void __launch_bounds__(256)
+upsample_ce_bwd_x4_kernel(const float* __restrict__ x, int ldx, int hin, int win, int n_valid, int C, int Cpad,
+                          const long long* __restrict__ labels, int ignore_index, const float* __restrict__ lse,
+                          const float* __restrict__ loss_and_count, const float* __restrict__ gscale,
+                          float* __restrict__ dx, int lddx, int tiles_x) {
+  extern __shared__ __align__(16) unsigned char uce_smem[];
+  float* lse_s = reinterpret_cast<float*>(uce_smem);
+  short* lab_s = reinterpret_cast<short*>(lse_s + UCE_R * UCE_R);
+  float* xs = reinterpret_cast<float*>(lab_s + UCE_R * UCE_R);
+  float* gs = xs + UCE_H * UCE_H * UCE_CC;
+  const int hout = 4 * hin, wout = 4 * win;
+  const int img = blockIdx.y;
+  const int y0 = (blockIdx.x / tiles_x) * UCE_T, x0 = (blockIdx.x % tiles_x) * UCE_T;
+  const int oy0 = 4 * y0 - 2, ox0 = 4 * x0 - 2;
+  const int tid = threadIdx.x;
+  const float sh_ = 0.25f, sw_ = 0.25f;
+  if (img >= n_valid) {  // zero-weighted half of the batch (trainer_cavp_vpo_mono.py:171): exact zeros
+    for (int i = tid; i < UCE_T * UCE_T * Cpad; i += 256) {
+      const int ch = i % Cpad, pp = i / Cpad;
+      const int iy = y0 + pp / UCE_T, ix = x0 + pp % UCE_T;
+      if (iy < hin && ix < win) dx[((static_cast<long long>(img) * hin + iy) * win + ix) * lddx + ch] = 0.f;
+    }
+    return;
+  }
+  const float coef = (gscale ? gscale[0] : 1.f) / loss_and_count[1];
+  const long long plane = static_cast<long long>(hout) * wout;
+  for (int i = tid; i < UCE_R * UCE_R; i += 256) {
+    const int oy = oy0 + i / UCE_R, ox = ox0 + i % UCE_R;
+    float l = 0.f;
+    short lb = -1;
+    if (oy >= 0 && oy < hout && ox >= 0 && ox < wout) {
+      const long long o = img * plane + static_cast<long long>(oy) * wout + ox;
+      const long long lab = labels[o];
+      l = lse[o];
+      lb = (lab == ignore_index || lab < 0 || lab >= C) ? static_cast<short>(-1) : static_cast<short>(lab);
+    }
+    lse_s[i] = l;
+    lab_s[i] = lb;
+  }
+  // per-thread gather weights of phase C: items (pp, cc) = (tid >> 3) + 32 k, tid & 7
+  const int cc = tid & 7;
+  for (int c0 = 0; c0 < Cpad; c0 += UCE_CC) {
+    __syncthreads();  // previous chunk's phase C is done with xs / gs (first pass: lse_s / lab_s are written)
+    for (int i = tid; i < UCE_H * UCE_H * UCE_CC; i += 256) {
+      const int ch = i % UCE_CC, pp = i / UCE_CC;
+      int iy = y0 - 1 + pp / UCE_H, ix = x0 - 1 + pp % UCE_H;
+      iy = min(max(iy, 0), hin - 1);
+      ix = min(max(ix, 0), win - 1);
+      xs[i] = (c0 + ch < C) ? __ldg(x + ((static_cast<long long>(img) * hin + iy) * win + ix) * ldx + c0 + ch) : 0.f;
+    }
+    __syncthreads();
+    for (int i = tid; i < UCE_R * UCE_R * UCE_CC; i += 256) {
+      const int ch = i % UCE_CC, o = i / UCE_CC;
+      const int lb = lab_s[o];
+      float g = 0.f;
+      if (lb >= 0 && c0 + ch < C) {
+        const int oy = oy0 + o / UCE_R, ox = ox0 + o % UCE_R;
+        const Lerp ly = lerp_index(oy, hin, sh_, 0), lx = lerp_index(ox, win, sw_, 0);
+        const int r0 = (ly.i0 - (y0 - 1)) * UCE_H, r1 = (ly.i1 - (y0 - 1)) * UCE_H;
+        const int q0 = lx.i0 - (x0 - 1), q1 = lx.i1 - (x0 - 1);
+        const float v = bilerp(ly, lx, xs[(r0 + q0) * UCE_CC + ch], xs[(r0 + q1) * UCE_CC + ch],
+                               xs[(r1 + q0) * UCE_CC + ch], xs[(r1 + q1) * UCE_CC + ch]);
+        g = expf(v - lse_s[o]) - (c0 + ch == lb ? 1.f : 0.f);
+      }
+      gs[o * UCE_GS + ch] = g;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int pp = (tid >> 3) + 32 * k;
+      const int py = pp / UCE_T, px = pp % UCE_T;
+      const int iy = y0 + py, ix = x0 + px;
+      if (iy >= hin || ix >= win) continue;
+      float wy[8], wx[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int oy = 4 * iy - 2 + j, ox = 4 * ix - 2 + j;
+        wy[j] = 0.f;
+        wx[j] = 0.f;
+        if (oy >= 0 && oy < hout) {
+          const Lerp l = lerp_index(oy, hin, sh_, 0);
+          wy[j] = (l.i0 == iy ? l.w0 : 0.f) + (l.i1 == iy ? l.w1 : 0.f);
+        }
+        if (ox >= 0 && ox < wout) {
+          const Lerp l = lerp_index(ox, win, sw_, 0);
+          wx[j] = (l.i0 == ix ? l.w0 : 0.f) + (l.i1 == ix ? l.w1 : 0.f);
+        }
+      }
+      float acc = 0.f;
+#pragma unroll
+      for (int jy = 0; jy < 8; ++jy) {
+        const float* row = gs + ((4 * py + jy) * UCE_R + 4 * px) * UCE_GS + cc;
+        float t = 0.f;
+#pragma unroll
+        for (int jx = 0; jx < 8; ++jx) t = fmaf(wx[jx], row[jx * UCE_GS], t);
+        acc = fmaf(wy[jy], t, acc);
+      }
+      if (c0 + cc < Cpad)
+        dx[((static_cast<long long>(img) * hin + iy) * win + ix) * lddx + c0 + cc] = (c0 + cc < C) ? acc * coef : 0.f;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ contrastive
 // anchors[i][:] = f[pix[i]][:] / max(||f[pix[i]]||, 1e-12)   (F.normalize over channels, then the gather of
 // contrastive_aud.py:100-135).  One warp per anchor.  pix indexes pixels of the whole [rows*h*w] NHWC buffer.
@@ -338,6 +456,17 @@ extern "C" int cavp_upsample_ce_bwd(const float* x, int ldx, int hin, int win, i
                                     void* stream) {
   if (!x || !labels || !lse || !loss_and_count || !dx) return CAVP_ERR_NULL;
   if (n <= 0 || n_valid < 0 || n_valid > n || C <= 0 || Cpad < C || ldx < C || lddx < Cpad) return CAVP_ERR_ARG;
+  static const bool no_tiled = getenv("CAVP_CE_BWD_GENERIC") != nullptr;  // force the generic kernel (tests)
+  if (hout == 4 * hin && wout == 4 * win && C < 32768 && !no_tiled) {
+    auto kern = upsample_ce_bwd_x4_kernel;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, UCE_SMEM);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    const int tiles_x = (win + UCE_T - 1) / UCE_T, tiles_y = (hin + UCE_T - 1) / UCE_T;
+    kern<<<dim3(tiles_x * tiles_y, n), 256, UCE_SMEM, ST(stream)>>>(x, ldx, hin, win, n_valid, C, Cpad, labels,
+                                                                   ignore_index, lse, loss_and_count, gscale, dx, lddx,
+                                                                   tiles_x);
+    CAVP_LAUNCH_CHECK();
+  }
   upsample_ce_bwd_kernel<<<grid_for(static_cast<long long>(n) * hin * win * Cpad, 256, 16), 256, 0, ST(stream)>>>(
       x, ldx, hin, win, hout, wout, n, n_valid, C, Cpad, lerp_scale(hin, hout, 0), lerp_scale(win, wout, 0), labels,
       ignore_index, lse, loss_and_count, gscale, dx, lddx);

@@ -27,7 +27,7 @@ def pad4(c):
 class Act:
     """NHWC activation view: storage `buf` [n*h*w, ld] (contiguous rows), channels [off, off+c)."""
 
-    __slots__ = ("buf", "n", "h", "w", "c", "off", "grad", "parent", "needs_grad")
+    __slots__ = ("buf", "n", "h", "w", "c", "off", "grad", "parent", "needs_grad", "want_split", "split")
 
     def __init__(self, buf, n, h, w, c, off=0, parent=None, needs_grad=True):
         assert buf.dim() == 2 and buf.shape[0] == n * h * w, (tuple(buf.shape), n, h, w)
@@ -35,6 +35,8 @@ class Act:
         self.grad = None
         self.parent = parent
         self.needs_grad = needs_grad
+        self.want_split = False  # a consumer's weight-gradient kernel wants d(this) as a dense TF32 hi | lo split
+        self.split = None        # (on a gradient Act) that split, [2, rows, c], written by the kernel that produced it
 
     @property
     def ld(self):
@@ -580,6 +582,8 @@ class Graph:
             else:
                 stats = stats_buf  # (tensor [nparts, 2, ldstat], pointer offset to our columns, nparts, ldstat)
                 assert stats[2] == nparts
+        if self.train and wr.param.requires_grad and y.off == 0 and y.ld == co and self.wgrad_via_tma(M, co, K):
+            y.want_split = True  # BatchNorm's backward then emits d(y) together with its TF32 split
         splits = self.fwd_splits(M, co, K)
         if splits > 1 and (save_pre or res_mod or res_div):
             splits = 1
@@ -667,8 +671,10 @@ class Graph:
                         self.call("cavp_zero", dwk.data_ptr(), dwk.numel() * 4)
                     if self.wgrad_via_tma(M, co, K):
                         # dY pre-split once (dense hi | lo) and fetched by TMA by every one of the K/128 column tiles
-                        gsp = self.empty(2, M, co)
-                        self.call("cavp_split_tf32_2d", g.ptr, g.ld, M, co, gsp[0].data_ptr(), gsp[1].data_ptr())
+                        gsp = g.split if (g is dy and g.split is not None) else None
+                        if gsp is None:
+                            gsp = self.empty(2, M, co)
+                            self.call("cavp_split_tf32_2d", g.ptr, g.ld, M, co, gsp[0].data_ptr(), gsp[1].data_ptr())
                         self.work(flops=2.0 * M * co * K,
                                   tag=f"wgrad(tma) P{M} Cout{co} K{K} k{r} s{stride} d{dil} splits{wsplits}")
                         self.call("cavp_igemm_wgrad_tma", gsp[0].data_ptr(), gsp[0].numel(), x.ptr, dwk.data_ptr(), x.n,
@@ -757,10 +763,15 @@ class Graph:
                 if acc_r:
                     tmp = new_act(res.n, res.h, res.w, res.c, self.device)
             tgt = tmp if tmp is not None else dres
+            hi_ptr = lo_ptr = 0
+            if y.want_split and dy.off == 0 and dy.ld == C:
+                dy.split = self.empty(2, M, C)
+                hi_ptr = dy.split[0].data_ptr()
+                lo_ptr = dy.split[1].data_ptr() if self.prec_wg == 2 else 0  # plain TF32 reads the hi part only
             self.call("cavp_bn_bwd_apply", dz.ptr, dz.ld, 0 if zin is None else zin.ptr, 0 if zin is None else zin.ld,
                       y.ptr, y.ld, coeffs[0].data_ptr(), coeffs[1].data_ptr(), bn.weight.data_ptr(), sums.data_ptr(),
                       1.0 / count, M, C, act, LEAKY_SLOPE, dy.ptr, dy.ld, 0 if tgt is None else tgt.ptr,
-                      0 if tgt is None else tgt.ld, zs, zb, count_dev)
+                      0 if tgt is None else tgt.ld, zs, zb, count_dev, hi_ptr, lo_ptr)
             if tmp is not None:
                 self.add_act(dres, tmp)
         self.tape.append(bwd)

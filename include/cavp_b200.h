@@ -124,8 +124,9 @@ int cavp_partials_sum(const float* partials, int nparts, int ldp, int C, int nk,
 int cavp_bn_bwd_apply(const float* dz, int lddz, const float* z, int ldz, const float* y, int ldy, const float* mean,
                       const float* invstd, const float* gamma, const float* sums, float inv_count, long long rows, int C,
                       int act, float slope, float* dy, int lddy, float* dres, int lddres, const float* zscale,
-                      const float* zshift, const double* count_dev, void* stream);
-/* ^ count_dev != NULL: 1/count is taken from device memory (the all-reduced count of SyncBatchNorm) instead of inv_count */
+                      const float* zshift, const double* count_dev, float* dy_hi, float* dy_lo, void* stream);
+/* ^ count_dev != NULL: 1/count is taken from device memory (the all-reduced count of SyncBatchNorm) instead of inv_count.
+ *   dy_hi / dy_lo != NULL: also write the dense [rows][C] TF32 split of dy (the operand of cavp_igemm_wgrad_tma). */
 
 /* ---- pooling (F.max_pool2d resnet.py:189 / vgg.py:30; ASPP global pooling encoder_decoder.py:158-164;
  *      AdaptiveMaxPool2d audio_network.py:24) ------------------------------------------------------------------- */
