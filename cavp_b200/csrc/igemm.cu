@@ -6,6 +6,7 @@
 #include "igemm_ws2.cuh"
 #include "igemm_wgrad2.cuh"
 #include "igemm_bf16.cuh"
+#include "igemm_ws2x.cuh"
 #include "../../include/cavp_b200.h"
 
 namespace cavp {
@@ -127,6 +128,34 @@ static int launch_igemm_ws2(const IgemmParams& p, const CUtensorMap& tm_hi, cons
   return static_cast<int>(cudaGetLastError());
 }
 
+// 256-column CTA-pair kernel (fp32-parity mode, N % 256 == 0)
+static int launch_igemm_ws2x(const IgemmParams& p, const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, cudaStream_t st) {
+  auto kern = igemm_ws2x_kernel;
+  static int max_pairs_dev[MAX_DEVICES] = {};
+  int& max_pairs = max_pairs_dev[current_device()];
+  if (max_pairs == 0) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WxCfg::SMEM_BYTES);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(148, 1, 1);
+    cfg.blockDim = dim3(WS_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = WxCfg::SMEM_BYTES;
+    int n = 0;
+    e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+    if (e != cudaSuccess || n < 1) {
+      cudaGetLastError();
+      n = 74;
+    }
+    max_pairs = n;
+  }
+  const int m_tiles = (p.M + BM - 1) / BM;
+  const int m_pairs = (m_tiles + 1) / 2;
+  const int total_work = m_pairs * p.n_tiles * p.splits;
+  const int pairs = total_work < max_pairs ? total_work : max_pairs;
+  kern<<<2 * pairs, WS_THREADS, WxCfg::SMEM_BYTES, st>>>(p, tm_hi, tm_lo, total_work, m_pairs);
+  return static_cast<int>(cudaGetLastError());
+}
+
 template <int PREC>
 static int launch_wgrad2(const IgemmParams& p, const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, cudaStream_t st) {
   using Cfg = Wg2Cfg<PREC>;
@@ -223,6 +252,21 @@ static int dispatch(IgemmParams& p, int prec, long long b_lo_off, cudaStream_t s
       const int pair_items = ((m_tiles_ + 1) / 2) * ((p.Ncols + 127) / 128) * p.splits;
       int sched = prec == 1 ? 1 : (heavy_epilogue ? 0 : ((bn == 128 && m_tiles_ >= 2 && pair_items >= 148) ? 2 : 1));
       if (ws_env) sched = ws_env[0] - '0';
+      if (sched == 2 && bn == 128 && prec == 2 && ws2x_epilogue_ok(p)) {
+        // 256-column pair tiles (igemm_ws2x.cuh) when the halved number of work items still fills the 74 TPCs evenly
+        static const char* x_env = getenv("CAVP_IGEMM_BN256");
+        const int items = ((m_tiles_ + 1) / 2) * (p.Ncols / 256) * p.splits;
+        const int waves = (items + 73) / 74;
+        const bool fill_ok = items >= 74 * 6 || items * 100 >= waves * 74 * 85;
+        if (x_env ? x_env[0] != '0' : fill_ok) {
+          p.n_tiles = p.Ncols / 256;
+          rc = make_weight_tmap(&tm_hi, p.w, p.Ncols, p.K, p.ldw, 128);
+          if (rc) return rc;
+          rc = make_weight_tmap(&tm_lo, p.w + b_lo_off, p.Ncols, p.K, p.ldw, 128);
+          if (rc) return rc;
+          return launch_igemm_ws2x(p, tm_hi, tm_lo, st);
+        }
+      }
       if (sched == 2 && bn == 128) {  // CTA-pair kernel: each CTA fetches half of the weight rows
         // 160-column tiles when they pad N less than 128-column tiles do (N = 304: 2 x 160 = 320 instead of 3 x 128 = 384)
         static const char* bn_env = getenv("CAVP_IGEMM_BN160");

@@ -56,6 +56,9 @@ def cl(m):
     (64, 128, 1, 2, 0, 1, 2, 12, 12, False),
     (256, 48, 3, 1, 4, 4, 1, 10, 10, False),
     (3, 64, 3, 2, 1, 1, 2, 16, 16, False),
+    (64, 256, 3, 1, 1, 1, 4, 30, 30, False),   # N = 256: eligible for the 256-column pair tile (forced-schedule runs)
+    (304, 256, 3, 1, 1, 1, 2, 28, 28, False),  # decoder conv: K = 2736 (K tail inside a promotion unit)
+    (96, 512, 3, 2, 1, 1, 3, 17, 15, True),    # two 256-column tiles, stride 2, ragged last row tile, residual in BN
 ])
 def test_conv_bn_relu_train(cin, cout, k, stride, pad, dil, n, h, w, use_res):
     torch.manual_seed(0)
@@ -113,6 +116,59 @@ def test_conv_bn_eval_fused():
                               bn.running_mean.double().cpu(), bn.running_var.double().cpu(), bn.weight.double().cpu(),
                               bn.bias.double().cpu(), False, 0.1, bn.eps))
     assert rel_err(back(za), ref) < TOL
+
+
+def test_conv_n256_eval_epilogue_dgrad_accumulate_and_splitk():
+    """Shapes with N % 256 == 0 on both sides (eligible for the 256-column pair tile under CAVP_IGEMM_BN256=1, see
+    tests/test_forced_schedules_gpu.py): eval-mode folded BN + LeakyReLU epilogue, a data gradient that accumulates in
+    place into an existing gradient (two consumers of one tensor), and the deterministic split-K slabs of a tiny map."""
+    from cavp_b200.engine import ACT_LEAKY
+    torch.manual_seed(11)
+    conv = cl(nn.Conv2d(256, 256, 3, 1, 2, 2, bias=False)).cuda()
+    bn = nn.BatchNorm2d(256).cuda()
+    bn.weight.data.uniform_(0.5, 1.5); bn.bias.data.normal_(0, 0.1)
+    bn.running_mean.normal_(0, 0.1); bn.running_var.uniform_(0.5, 1.5)
+    x = torch.randn(3, 256, 13, 11)
+    g = _g(train=False)
+    za = g.conv_bn(to_act(g, x), conv.weight, bn, stride=1, pad=2, dil=2, act=ACT_LEAKY)
+    ref = F.leaky_relu(F.batch_norm(F.conv2d(x.double(), conv.weight.double().cpu(), None, 1, 2, 2),
+                                    bn.running_mean.double().cpu(), bn.running_var.double().cpu(),
+                                    bn.weight.double().cpu(), bn.bias.double().cpu(), False, 0.1, bn.eps), 0.01)
+    assert rel_err(back(za), ref) < TOL
+    # two convs read the same input: the second data gradient accumulates in place (igemm residual == output)
+    c1, c2 = cl(nn.Conv2d(256, 64, 3, 1, 1, 1, bias=False)).cuda(), cl(nn.Conv2d(256, 512, 1, 1, 0, 1, bias=False)).cuda()
+    xr = x.double().requires_grad_(True)
+    y1 = F.conv2d(xr, c1.weight.double().cpu(), None, 1, 1, 1)
+    y2 = F.conv2d(xr, c2.weight.double().cpu())
+    d1, d2 = torch.randn_like(y1), torch.randn_like(y2)
+    (y1 * d1).sum().backward(retain_graph=True)
+    (y2 * d2).sum().backward()
+    g = _g()
+    xa = to_act(g, x)
+    a1, _ = g.conv(xa, c1.weight, pad=1)
+    a2, _ = g.conv(xa, c2.weight)
+    assert rel_err(back(a1), y1) < TOL and rel_err(back(a2), y2) < TOL
+    seed(g, a1, d1)
+    seed(g, a2, d2)
+    g.backward()
+    assert rel_err(back(g.grad_of(xa)), xr.grad) < TOL
+    # tiny map, long K: forward split-K (private slabs, fixed-order sum) and dgrad split-K (red.add)
+    c3 = cl(nn.Conv2d(1024, 256, 3, 1, 1, 1, bias=False)).cuda()
+    x3 = torch.randn(2, 1024, 6, 5)
+    x3r = x3.double().requires_grad_(True)
+    y3 = F.conv2d(x3r, c3.weight.double().cpu(), None, 1, 1, 1)
+    d3 = torch.randn_like(y3)
+    y3.backward(d3)
+    g = _g()
+    x3a = to_act(g, x3)
+    a3, _ = g.conv(x3a, c3.weight, pad=1)
+    assert rel_err(back(a3), y3) < TOL
+    seed(g, a3, d3)
+    g.backward()
+    assert rel_err(back(g.grad_of(x3a)), x3r.grad) < TOL
+    # dW[o][i][ky][kx] = sum_{n,y,x} d3[n][o][y][x] * x3[n][i][y+ky-1][x+kx-1]  ==  a correlation of x3 with d3
+    wref = F.conv2d(x3.double().transpose(0, 1), d3.transpose(0, 1), None, 1, 1, 1).transpose(0, 1)
+    assert rel_err(g.param_grads[id(c3.weight)], wref) < TOL
 
 
 def test_linear_bias_gelu_and_residual():
