@@ -443,21 +443,26 @@ def run_ours(args):
             with open(args.dump_profile, "w") as f:
                 for ms_, name, tag, fl in rows_[:150]:
                     f.write(f"{ms_:8.3f} ms  {fl / ms_ / 1e9 if ms_ > 0 else 0:7.1f} TF  {name}  {tag}\n")
-        ig = [agg.get(k, [0, 0, 0, 0]) for k in ("cavp_igemm", "cavp_igemm_wgrad", "cavp_igemm_wgrad_tma")]
+        ig = [agg.get(k, [0, 0, 0, 0]) for k in ("cavp_igemm", "cavp_igemm_wgrad", "cavp_igemm_wgrad_tma",
+                                                 "cavp_igemm_bf16", "cavp_igemm_wgrad_bf16")]
         ig_ms, ig_n, ig_fl = sum(v[0] for v in ig), sum(v[1] for v in ig), sum(v[2] for v in ig)
         # DRAM traffic per launch of the same kernels, from the committed ncu launch list of this command
         # (profiles/r01_ncu_step_summary.json, written by tools/ncu_summarize.py; ncu counters cannot be read live)
         traffic, traffic_src = None, None
-        try:
-            summ = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_step_summary.json")))["kernels"]
-            ig = [v for k, v in summ.items() if "igemm" in k]
-            n_l = sum(v["launches"] for v in ig)
-            if n_l:
-                traffic = 1e6 * sum(v["dram_read_MB"] + v["dram_write_MB"] for v in ig) / n_l
-                traffic_src = ("profiles/r01_ncu_step_summary.json: dram__bytes_read.sum + dram__bytes_write.sum over "
-                               f"{n_l} igemm launches of the bench command, bytes per launch")
-        except Exception:
-            pass
+        for prof_name in ("r02_ncu_step_summary.json", "r01_ncu_step_summary.json"):
+            if args.prec != 2:
+                break  # the committed launch list is of the default (fp32-parity) command
+            try:
+                summ = json.load(open(os.path.join(ROOT, "profiles", prof_name)))["kernels"]
+                igk = [v for k, v in summ.items() if "igemm" in k]
+                n_l = sum(v["launches"] for v in igk)
+                if n_l:
+                    traffic = 1e6 * sum(v["dram_read_MB"] + v["dram_write_MB"] for v in igk) / n_l
+                    traffic_src = (f"profiles/{prof_name}: dram__bytes_read.sum + dram__bytes_write.sum over "
+                                   f"{n_l} igemm launches of the bench command, bytes per launch")
+                    break
+            except Exception:
+                continue
         peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
         achieved = ig_fl / (ig_ms / 1e3) / 1e12 if ig_ms else 0.0
         roofline = {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM tile kernels igemm_ws / igemm_ws2 / igemm_kernel (cavp_igemm + cavp_igemm_wgrad[_tma])",
@@ -465,7 +470,10 @@ def run_ours(args):
                     "traffic": traffic, "traffic_source": traffic_src, "launches_per_step": ig_n, "avg_launch_ms": ig_ms / max(ig_n, 1),
                     "flop_per_step_executed": ig_fl, "share_of_kernel_time": ig_ms / total_ms if total_ms else None,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (measured)" if peaks else "fallback",
-                    "note": "fp32-parity mode issues 3 TF32 MMAs per product (<= 1/6 of the bf16 peak by construction)"}
+                    "note": {2: "fp32-parity mode issues 3 TF32 MMAs per product (<= 1/6 of the bf16 peak by construction)",
+                             1: "plain TF32: one TF32 MMA per product (<= 1/2 of the bf16 peak by construction)",
+                             3: "bf16 operands for forward / dgrad / large weight gradients (kind::f16), TF32 for the "
+                                "small weight gradients; fp32 activations are converted by the producer warps"}[args.prec]}
         gate = agg.get("cavp_gate_fwd")
         if gate and gate[0] > 0:
             hbm = peaks.get("hbm_gbs", 6650.0)
@@ -481,8 +489,9 @@ def run_ours(args):
         tf32_peak = measure_tf32_peak(dev)
         stock = gpu_stock_baseline(dev, B)
         if roofline is not None and tf32_peak:
-            ceil3 = tf32_peak["tf32_tflops_sustained"] / 3.0
             roofline["tf32_peak_measured"] = tf32_peak
+        if roofline is not None and tf32_peak and args.prec == 2:
+            ceil3 = tf32_peak["tf32_tflops_sustained"] / 3.0
             roofline["frac_of_3xtf32_ceiling"] = roofline["achieved"] / ceil3
             roofline["note"] += ("; against the TF32 matmul peak measured in this run (sustained / 3 = %.0f TFLOP/s) "
                                  "the tile kernels reach frac_of_3xtf32_ceiling" % ceil3)

@@ -390,7 +390,8 @@ bn_bwd_apply_kernel(const float* __restrict__ dz, int lddz, const float* __restr
                     const float* __restrict__ sums, float inv_count, long long rows, int C4, int act,
                     float slope, float* __restrict__ dy, int lddy, float* __restrict__ dres,
                     int lddres, const float* __restrict__ zscale, const float* __restrict__ zshift, int LC,
-                    const double* __restrict__ count_dev, float* __restrict__ dy_hi, float* __restrict__ dy_lo) {
+                    const double* __restrict__ count_dev, float* __restrict__ dy_hi, float* __restrict__ dy_lo,
+                    int split_bf16) {
   if (count_dev) inv_count = static_cast<float>(1.0 / count_dev[0]);  // SyncBatchNorm: the all-reduced global count
   const int cl = threadIdx.x & (LC - 1), rl = threadIdx.x / LC;
   const int nrl = 256 / LC;
@@ -431,7 +432,13 @@ bn_bwd_apply_kernel(const float* __restrict__ dz, int lddz, const float* __restr
     o.z = ga.z * is.z * (g.z - sg.z * inv_count - (yy.z - mu.z) * is.z * sgx.z * inv_count);
     o.w = ga.w * is.w * (g.w - sg.w * inv_count - (yy.w - mu.w) * is.w * sgx.w * inv_count);
     *reinterpret_cast<float4*>(dy + r * lddy + c) = o;
-    if (dy_hi) {
+    if (dy_hi && split_bf16) {  // bf16 row: the dense bf16 copy of dy the bf16 weight-gradient kernel fetches by TMA
+      __nv_bfloat162 a = __floats2bfloat162_rn(o.x, o.y), b = __floats2bfloat162_rn(o.z, o.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&a);
+      pk.y = *reinterpret_cast<uint32_t*>(&b);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(dy_hi) + r * C + c) = pk;
+    } else if (dy_hi) {
       // the TF32 hi | lo split of dy, dense [rows][C]: the TMA-fed weight-gradient kernels read it directly, so the
       // separate split pass (one more read of dy) disappears
       const float h0 = tf32_rn_dev(o.x), h1 = tf32_rn_dev(o.y), h2 = tf32_rn_dev(o.z), h3 = tf32_rn_dev(o.w);
@@ -787,12 +794,12 @@ extern "C" int cavp_bn_bwd_apply(const float* dz, int lddz, const float* z, int 
                                  const float* mean, const float* invstd, const float* gamma, const float* sums,
                                  float inv_count, long long rows, int C, int act, float slope, float* dy, int lddy,
                                  float* dres, int lddres, const float* zscale, const float* zshift,
-                                 const double* count_dev, float* dy_hi, float* dy_lo, void* stream) {
+                                 const double* count_dev, float* dy_hi, float* dy_lo, int split_bf16, void* stream) {
   if ((C & 3) || (lddz & 3) || (ldy & 3) || (lddy & 3)) return CAVP_ERR_ALIGN;
   const int LC = pick_lc(C / 4);
   bn_bwd_apply_kernel<<<colgrid(rows, C / 4, LC), 256, 0, ST(stream)>>>(
       dz, lddz, z, ldz, y, ldy, mean, invstd, gamma, sums, inv_count, rows, C / 4, act, slope, dy, lddy, dres, lddres,
-      zscale, zshift, LC, count_dev, dy_hi, dy_lo);
+      zscale, zshift, LC, count_dev, dy_hi, dy_lo, split_bf16);
   CAVP_LAUNCH_CHECK();
 }
 extern "C" int cavp_maxpool_fwd(const float* x, int ldx, float* y, int ldy, int* idx, int n, int h, int w, int c, int k,

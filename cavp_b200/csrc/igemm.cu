@@ -7,6 +7,8 @@
 #include "igemm_wgrad2.cuh"
 #include "igemm_bf16.cuh"
 #include "igemm_ws2x.cuh"
+#include "igemm_wgrad_bf16.cuh"
+#include <cuda_bf16.h>
 #include "../../include/cavp_b200.h"
 
 namespace cavp {
@@ -349,6 +351,36 @@ __global__ void split_tf32_2d_kernel(const float* __restrict__ src, int ld, long
   }
 }
 
+// strided fp32 [rows][ld] -> dense bf16 [rows][cols] (the dY operand of the bf16 weight-gradient kernel)
+__global__ void cvt_bf16_2d_kernel(const float* __restrict__ src, int ld, long long rows, int cols4,
+                                   __nv_bfloat16* __restrict__ dst) {
+  const long long n4 = rows * cols4;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / cols4;
+    const int c = static_cast<int>(i - r * cols4);
+    const float4 v = *reinterpret_cast<const float4*>(src + r * ld + c * 4);
+    uint2 o;
+    o.x = cvt_bf16x2(v.x, v.y);
+    o.y = cvt_bf16x2(v.z, v.w);
+    reinterpret_cast<uint2*>(dst)[i] = o;
+  }
+}
+
+// dense bf16 [P][cout] matrix, box = 64 channels x 64 pixels, 128-byte swizzle = the MN-major bf16 UMMA operand layout
+static int make_dy_tmap_bf16(CUtensorMap* tm, const void* dy, long long P, int cout) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return CAVP_ERR_ARG;
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cout), static_cast<cuuint64_t>(P)};
+  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(cout) * 2};
+  cuuint32_t box[2] = {64, static_cast<cuuint32_t>(WgBf16Cfg::KPIX)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(dy), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 1000 + static_cast<int>(r);
+}
+
 static void fill_divs(IgemmParams& p) {
   p.div_howo = make_fastdiv(static_cast<uint32_t>(p.Ho * p.Wo));
   p.div_wo = make_fastdiv(static_cast<uint32_t>(p.Wo));
@@ -494,5 +526,56 @@ extern "C" int cavp_split_tf32(const float* w, float* hi, float* lo, long long n
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
   split_tf32_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(w, hi, lo, n / 4);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int cavp_cvt_bf16_2d(const float* src, int ld, long long rows, int cols, void* dst, void* stream) {
+  if (!src || !dst) return CAVP_ERR_NULL;
+  if ((cols & 3) || (ld & 3) || (reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst) & 7))
+    return CAVP_ERR_ALIGN;
+  long long blocks = (rows * (cols / 4) + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  cvt_bf16_2d_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, ld, rows, cols / 4, static_cast<__nv_bfloat16*>(dst));
+  return static_cast<int>(cudaGetLastError());
+}
+
+// bf16 weight gradient (cavp_prec = 3): dy_bf16 = dense bf16 [P][cout]; x = fp32 NHWC source of the im2col operand
+extern "C" int cavp_igemm_wgrad_bf16(const void* dy_bf16, const float* x, float* dw, int nimg, int hs, int ws, int c,
+                                     int ldx, int ho, int wo, int r, int s, int stride, int pad, int dil, int cout,
+                                     int splits, void* stream) {
+  if (!dy_bf16 || !x || !dw) return CAVP_ERR_NULL;
+  if ((c & 7) || (ldx & 3) || (cout & 7)) return CAVP_ERR_ALIGN;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(dy_bf16) & 15)) return CAVP_ERR_ALIGN;
+  if (cout <= BM) return CAVP_ERR_ARG;  // the pair tile is 256 output channels; small layers use the TF32 kernels
+  const long long P = static_cast<long long>(nimg) * ho * wo;
+  if (P <= 0 || P >= (1ll << 31) || static_cast<long long>(nimg) * hs * ws >= (1ll << 31)) return CAVP_ERR_ARG;
+  IgemmParams p{};
+  p.x = x; p.w = nullptr; p.y = dw;
+  p.Nimg = nimg; p.Hs = hs; p.Ws = ws; p.C = c; p.ldx = ldx; p.Ho = ho; p.Wo = wo;
+  p.R = r; p.S = s; p.stride = stride; p.pad = pad; p.dil = dil;
+  p.M = cout; p.Ncols = r * s * c; p.K = r * s * c; p.ldw = cout; p.ldy = r * s * c;
+  p.red_len = static_cast<int>(P);
+  p.num_kb = (p.red_len + WgBf16Cfg::KPIX - 1) / WgBf16Cfg::KPIX;
+  p.splits = splits < 1 ? 1 : (splits > p.num_kb ? p.num_kb : splits);
+  p.n_tiles = (p.Ncols + WgBf16Cfg::BN - 1) / WgBf16Cfg::BN;
+  fill_divs(p);
+  CUtensorMap tm;
+  memset(&tm, 0, sizeof(tm));
+  int rc = make_dy_tmap_bf16(&tm, dy_bf16, P, cout);
+  if (rc) return rc;
+  auto kern = igemm_wgrad_bf16_kernel;
+  static bool configured_dev[MAX_DEVICES] = {};
+  bool& configured = configured_dev[current_device()];
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WgBf16Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    configured = true;
+  }
+  const int m_tiles = (p.M + BM - 1) / BM;
+  const int m_pairs = (m_tiles + 1) / 2;
+  dim3 grid(static_cast<unsigned>(2 * m_pairs * p.n_tiles), static_cast<unsigned>(p.splits), 1);
+  kern<<<grid, CTA_THREADS, WgBf16Cfg::SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(p, tm);
   return static_cast<int>(cudaGetLastError());
 }

@@ -526,6 +526,12 @@ class Graph:
                 best, best_cost = s, cost
         return best
 
+    def wgrad_bf16_ok(self, cin, cout):
+        """bf16 row: weight gradients with bf16 operands (csrc/igemm_wgrad_bf16.cuh) inside that kernel's envelope."""
+        import os
+        return (self.prec == 3 and cin % 8 == 0 and cout % 8 == 0 and cout > 128
+                and os.environ.get("CAVP_WGRAD_BF16", "1") != "0")
+
     @staticmethod
     def wgrad_via_tma(P, cout, K):
         """The split pass over dY costs 12 B per element; it pays when enough column tiles (K / 128) re-read dY."""
@@ -582,8 +588,10 @@ class Graph:
             else:
                 stats = stats_buf  # (tensor [nparts, 2, ldstat], pointer offset to our columns, nparts, ldstat)
                 assert stats[2] == nparts
-        if self.train and wr.param.requires_grad and y.off == 0 and y.ld == co and self.wgrad_via_tma(M, co, K):
-            y.want_split = True  # BatchNorm's backward then emits d(y) together with its TF32 split
+        if self.train and wr.param.requires_grad and y.off == 0 and y.ld == co and (
+                self.wgrad_bf16_ok(x.c, co) or self.wgrad_via_tma(M, co, K)):
+            # BatchNorm's backward then emits d(y) together with its TF32 split / bf16 copy
+            y.want_split = "bf16" if self.wgrad_bf16_ok(x.c, co) else "tf32"
         splits = self.fwd_splits(M, co, K)
         if splits > 1 and (save_pre or res_mod or res_div):
             splits = 1
@@ -669,9 +677,18 @@ class Graph:
                     wsplits = self.wgrad_splits(M, co, K)
                     if wsplits > 1:
                         self.call("cavp_zero", dwk.data_ptr(), dwk.numel() * 4)
-                    if self.wgrad_via_tma(M, co, K):
+                    if self.wgrad_bf16_ok(x.c, co):
+                        g16 = g.split if (g is dy and g.split is not None and g.split.dtype == torch.bfloat16) else None
+                        if g16 is None:
+                            g16 = self.empty(M, co, dtype=torch.bfloat16)
+                            self.call("cavp_cvt_bf16_2d", g.ptr, g.ld, M, co, g16.data_ptr())
+                        self.work(flops=2.0 * M * co * K,
+                                  tag=f"wgrad(bf16) P{M} Cout{co} K{K} k{r} s{stride} d{dil} splits{wsplits}")
+                        self.call("cavp_igemm_wgrad_bf16", g16.data_ptr(), x.ptr, dwk.data_ptr(), x.n, x.h, x.w, x.c,
+                                  x.ld, ho, wo, r, s, stride, pad, dil, co, wsplits)
+                    elif self.wgrad_via_tma(M, co, K):
                         # dY pre-split once (dense hi | lo) and fetched by TMA by every one of the K/128 column tiles
-                        gsp = g.split if (g is dy and g.split is not None) else None
+                        gsp = g.split if (g is dy and g.split is not None and g.split.dtype == torch.float32) else None
                         if gsp is None:
                             gsp = self.empty(2, M, co)
                             self.call("cavp_split_tf32_2d", g.ptr, g.ld, M, co, gsp[0].data_ptr(), gsp[1].data_ptr())
@@ -763,15 +780,19 @@ class Graph:
                 if acc_r:
                     tmp = new_act(res.n, res.h, res.w, res.c, self.device)
             tgt = tmp if tmp is not None else dres
-            hi_ptr = lo_ptr = 0
+            hi_ptr = lo_ptr = split_bf16 = 0
             if y.want_split and dy.off == 0 and dy.ld == C:
-                dy.split = self.empty(2, M, C)
-                hi_ptr = dy.split[0].data_ptr()
-                lo_ptr = dy.split[1].data_ptr() if self.prec_wg == 2 else 0  # plain TF32 reads the hi part only
+                if y.want_split == "bf16":  # consumer = the bf16 weight-gradient kernel
+                    dy.split = self.empty(M, C, dtype=torch.bfloat16)
+                    hi_ptr, split_bf16 = dy.split.data_ptr(), 1
+                else:
+                    dy.split = self.empty(2, M, C)
+                    hi_ptr = dy.split[0].data_ptr()
+                    lo_ptr = dy.split[1].data_ptr() if self.prec_wg == 2 else 0  # plain TF32 reads the hi part only
             self.call("cavp_bn_bwd_apply", dz.ptr, dz.ld, 0 if zin is None else zin.ptr, 0 if zin is None else zin.ld,
                       y.ptr, y.ld, coeffs[0].data_ptr(), coeffs[1].data_ptr(), bn.weight.data_ptr(), sums.data_ptr(),
                       1.0 / count, M, C, act, LEAKY_SLOPE, dy.ptr, dy.ld, 0 if tgt is None else tgt.ptr,
-                      0 if tgt is None else tgt.ld, zs, zb, count_dev, hi_ptr, lo_ptr)
+                      0 if tgt is None else tgt.ld, zs, zb, count_dev, hi_ptr, lo_ptr, split_bf16)
             if tmp is not None:
                 self.add_act(dres, tmp)
         self.tape.append(bwd)

@@ -60,6 +60,13 @@ int cavp_igemm_bf16(const float* x, const float* w, const void* w_bf16, float* y
                     int wo, int r, int s, int stride, int pad, int dil, int dgrad, int ncols, int ldw, int ldy, int ldr,
                     int res_mod, int res_div, int ldstat, int act, float slope, int splits, long long b_lo_off,
                     void* stream);
+/* bf16 weight gradient of the bf16 row (cavp_prec = 3): dw[cout][r*s*c] (+)= dy^T * im2col(x) with bf16 operands
+ * (tcgen05.mma.kind::f16, both MN-major) and fp32 accumulation.  dy_bf16 = dense bf16 [P][cout] (cavp_cvt_bf16_2d, or
+ * written by cavp_bn_bwd_apply with split_mode 1); x = fp32 NHWC.  Needs c % 8 == 0, cout % 8 == 0, cout > 128;
+ * splits > 1 accumulates into a PRE-ZEROED dw. */
+int cavp_igemm_wgrad_bf16(const void* dy_bf16, const float* x, float* dw, int nimg, int hs, int ws, int c, int ldx, int ho,
+                          int wo, int r, int s, int stride, int pad, int dil, int cout, int splits, void* stream);
+int cavp_cvt_bf16_2d(const float* src, int ld, long long rows, int cols, void* dst, void* stream);
 /* cavp_igemm_wgrad: dw[cout][r*s*c] (+)= dy[P][cout]^T * im2col(x)[P][r*s*c]   (weight gradient; P = nimg*ho*wo).
  *   splits > 1 accumulates into a PRE-ZEROED dw. */
 int cavp_igemm_wgrad(const float* dy, const float* x, float* dw, int nimg, int hs, int ws, int c, int ldx, int ho,
@@ -124,9 +131,11 @@ int cavp_partials_sum(const float* partials, int nparts, int ldp, int C, int nk,
 int cavp_bn_bwd_apply(const float* dz, int lddz, const float* z, int ldz, const float* y, int ldy, const float* mean,
                       const float* invstd, const float* gamma, const float* sums, float inv_count, long long rows, int C,
                       int act, float slope, float* dy, int lddy, float* dres, int lddres, const float* zscale,
-                      const float* zshift, const double* count_dev, float* dy_hi, float* dy_lo, void* stream);
+                      const float* zshift, const double* count_dev, float* dy_hi, float* dy_lo, int split_bf16,
+                      void* stream);
 /* ^ count_dev != NULL: 1/count is taken from device memory (the all-reduced count of SyncBatchNorm) instead of inv_count.
- *   dy_hi / dy_lo != NULL: also write the dense [rows][C] TF32 split of dy (the operand of cavp_igemm_wgrad_tma). */
+ *   dy_hi / dy_lo != NULL: also write the dense [rows][C] TF32 split of dy (the operand of cavp_igemm_wgrad_tma);
+ *   split_bf16 != 0: dy_hi receives a dense bf16 [rows][C] copy instead (the operand of cavp_igemm_wgrad_bf16). */
 
 /* ---- pooling (F.max_pool2d resnet.py:189 / vgg.py:30; ASPP global pooling encoder_decoder.py:158-164;
  *      AdaptiveMaxPool2d audio_network.py:24) ------------------------------------------------------------------- */
