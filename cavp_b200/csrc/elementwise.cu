@@ -786,7 +786,27 @@ extern "C" int cavp_colreduce(const float* dz, int lddz, const float* z, int ldz
                                                  ldg, partials, ldp, zscale, zshift, LC);
   CAVP_LAUNCH_CHECK();
 }
+// few, large slabs (deterministic split-K: out = slab_0 + slab_1 + ... in that order): one float4 per thread and step
+__global__ void slab_sum_kernel(const float* __restrict__ slabs, int nslabs, long long slab_elems, long long n4,
+                                float* __restrict__ out) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    double a = 0.0, b = 0.0, c = 0.0, d = 0.0;
+    for (int k = 0; k < nslabs; ++k) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(slabs + k * slab_elems) + i);
+      a += v.x; b += v.y; c += v.z; d += v.w;
+    }
+    reinterpret_cast<float4*>(out)[i] =
+        make_float4(static_cast<float>(a), static_cast<float>(b), static_cast<float>(c), static_cast<float>(d));
+  }
+}
 extern "C" int cavp_partials_sum(const float* partials, int nparts, int ldp, int C, int nk, float* out, void* stream) {
+  if (nk == 1 && nparts <= 64 && C >= 16384 && (C & 3) == 0 && (ldp & 3) == 0 &&
+      ((reinterpret_cast<uintptr_t>(partials) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+    const long long n4 = C / 4;
+    slab_sum_kernel<<<grid_for(n4, 256, 16), 256, 0, ST(stream)>>>(partials, nparts, ldp, n4, out);
+    CAVP_LAUNCH_CHECK();
+  }
   partials_sum_kernel<<<(nk * C + 31) / 32, dim3(32, 32), 0, ST(stream)>>>(partials, nparts, ldp, C, nk, out);
   CAVP_LAUNCH_CHECK();
 }

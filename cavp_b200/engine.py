@@ -504,6 +504,16 @@ class Graph:
         bn = 128 if ncols > 64 else 64
         tiles = ((M + 127) // 128) * ((ncols + bn - 1) // bn)
         num_kb = (K + 31) // 32
+        if ncols % 256 == 0 and num_kb >= 128:
+            # long-K layers whose 256-column pair tiles (csrc/igemm_ws2x.cuh) would fill the 74 CTA pairs unevenly
+            # (ASPP 3x3 convs: 98 items): a deterministic split-K of 2-3 restores the fill at the price of one small
+            # slab-sum pass, and keeps them on the 256-column kernel (85 % instead of 66 % tensor-pipe active)
+            items = ((((M + 127) // 128) + 1) // 2) * (ncols // 256)
+            fill = lambda n: n / (((n + 73) // 74) * 74)
+            if 74 <= items < 74 * 6 and fill(items) < 0.85:
+                for sk in (2, 3):
+                    if fill(items * sk) >= 0.85:
+                        return sk
         if tiles >= 96 or num_kb < 16:
             return 1
         return max(1, min(num_kb // 8, (NUM_SMS + tiles - 1) // tiles))

@@ -73,11 +73,19 @@ class InfoNCE:
         self.S = g.empty(A, A4)
         a_act = Act(self.anchors, A, 1, 1, C, needs_grad=False)
         s_act = Act(self.S, A, 1, 1, A)
-        g._igemm(a_act, self.anchors, A, C, s_act, geom=(1, 1, 1, 1, 1, 0, 1))
+        # S = A A^T: the anchor matrix is also the weight operand - pre-split once (3 MB) so that it is fetched by TMA and
+        # the GEMM runs on the CTA-pair kernels (256-column tiles when A % 256 == 0) instead of the generic tile kernel
+        g._igemm(a_act, self._presplit(self.anchors), A, C, s_act, geom=(1, 1, 1, 1, 1, 0, 1))
         self.rows = g.empty(3, A)  # rowmax, rowneg, rowmean
         self.loss = g.empty(1)
         g.call("cavp_infonce_fwd", self.S.data_ptr(), A4, self.labels.data_ptr(), A, float(temperature),
                self.rows[0].data_ptr(), self.rows[1].data_ptr(), self.rows[2].data_ptr(), self.loss.data_ptr())
+
+    def _presplit(self, w):
+        """[hi | lo] TF32 split of a K-major operand -> (tensor, lo offset) as Graph._igemm takes it"""
+        sp = self.g.empty(2, w.shape[0], w.shape[1])
+        self.g.call("cavp_split_tf32", w.data_ptr(), sp[0].data_ptr(), sp[1].data_ptr(), w.numel())
+        return sp[0], w.numel()
 
     def backward(self, gscale, targets):
         """gscale: device tensor [1] (upstream gradient) or None.  targets: list of (grad_base_ptr, ld) aligned with
@@ -90,7 +98,8 @@ class InfoNCE:
         at = g.zeros(C, A4)
         g.call("cavp_transpose", self.anchors.data_ptr(), at.data_ptr(), A, C, C, A4, 1, 0, 0)
         d1 = g.empty(A, C)
-        g._igemm(Act(G, A, 1, 1, A4, needs_grad=False), at, C, A4, Act(d1, A, 1, 1, C), geom=(1, 1, 1, 1, 1, 0, 1))
+        g._igemm(Act(G, A, 1, 1, A4, needs_grad=False), self._presplit(at), C, A4, Act(d1, A, 1, 1, C),
+                 geom=(1, 1, 1, 1, 1, 0, 1))
         d2 = g.empty(A4, C)
         wsplits = Graph.wgrad_splits(A, A4, C)
         if wsplits > 1:
