@@ -48,6 +48,7 @@ CONFIGS = {
 CFG = dict(CONFIGS[1]["cfg"])
 WORKLOAD = CONFIGS[1]["workload"]
 METRIC = "AVS train-step images/sec @224^2 bs32/GPU"
+NCCL_MAX_CTAS_DEFAULT = 0  # chosen by measurement at 8 GPUs (profiles/README.md)
 FLOPS_PER_IMAGE = CONFIGS[1]["flops"]
 
 
@@ -312,7 +313,21 @@ def run_ours(args):
         if "NCCL_DEBUG_FILE" not in os.environ:  # NCCL writes to a per-rank file; it is copied to stderr below
             nccl_log = f"/tmp/cavp_nccl_rank{rank}_{os.getpid()}.log"
             os.environ["NCCL_DEBUG_FILE"] = nccl_log
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL's kernels and ours compete for SMs while a bucket's all-reduce overlaps the backward pass (our GEMM kernels
+        # are persistent, one CTA or CTA pair per SM / TPC): cap the collective's CTAs (CAVP_NCCL_MAX_CTAS, 0 = NCCL's choice)
+        max_ctas = int(os.environ.get("CAVP_NCCL_MAX_CTAS", str(NCCL_MAX_CTAS_DEFAULT)))
+        pg_opts = None
+        if max_ctas > 0:
+            try:
+                pg_opts = dist.ProcessGroupNCCL.Options()
+                pg_opts.config.max_ctas = max_ctas
+                pg_opts.config.min_ctas = min(max_ctas, 4)
+            except Exception:
+                pg_opts = None
+        if pg_opts is not None:
+            dist.init_process_group("nccl", device_id=dev, pg_options=pg_opts)
+        else:
+            dist.init_process_group("nccl", device_id=dev)
         probe = torch.ones(1, device=dev)
         dist.all_reduce(probe)  # forces communicator creation so that its INIT lines exist before the timed region
         torch.cuda.synchronize()
@@ -379,8 +394,28 @@ def run_ours(args):
         opt_a.step()
         launches[0] += res.launches + 2  # + the two fused optimiser kernels
         if not resident:
-            return torch.stack((res.l_ce.reshape(()), res.l_ctr.reshape(()))).tolist()  # D2H read of the step's result
+            # D2H read of the step's result, every step: the two losses go to a pinned slot with a non-blocking copy and
+            # are consumed on the host one step later (after the next step has been issued), the way a training loop
+            # logs its losses without draining the launch queue; the last step's losses are read inside the timed region
+            slot = readback["ring"][readback["n"] % 2]
+            slot["buf"].copy_(torch.stack((res.l_ce.reshape(()), res.l_ctr.reshape(()))), non_blocking=True)
+            slot["ev"].record(torch.cuda.current_stream(dev))
+            if readback["n"] > 0:
+                prev = readback["ring"][(readback["n"] - 1) % 2]
+                prev["ev"].synchronize()
+                readback["last"] = prev["buf"].tolist()
+            readback["n"] += 1
+            return None
         return res
+
+    readback = {"ring": [{"buf": torch.empty(2, dtype=torch.float32).pin_memory(), "ev": torch.cuda.Event()}
+                         for _ in range(2)], "n": 0, "last": None}
+
+    def drain_readback():
+        if readback["n"] > 0:
+            cur = readback["ring"][(readback["n"] - 1) % 2]
+            cur["ev"].synchronize()
+            readback["last"] = cur["buf"].tolist()
 
     def timed(resident):
         for _ in range(args.warmup):
@@ -396,6 +431,8 @@ def run_ours(args):
         t_host = time.perf_counter()
         for _ in range(args.steps):
             step(resident)
+        if not resident:
+            drain_readback()  # the last step's losses, still inside the timed region
         host_ms[0] = 1e3 * (time.perf_counter() - t_host) / args.steps  # time to ISSUE a step (no device sync)
         e1.record()
         torch.cuda.synchronize()
@@ -514,10 +551,17 @@ def run_ours(args):
                                             "dgrad GEMMs, TF32 weight gradients, fp32 activations / BN statistics / "
                                             "LayerNorm / losses; stems and classifier fp32-grade"}[args.prec],
                            "l2": "working set per step (>10 GB of activations) far exceeds the 126 MB L2; no flush needed",
-                           "bn": "local (per-rank) BatchNorm statistics"},
+                           "bn": "local (per-rank) BatchNorm statistics",
+                           "allreduce": (f"4 gradient buckets produced in place, NCCL all-reduce(AVG) of each bucket launched "
+                                         f"asynchronously from a backward-tape marker (overlaps the rest of the backward); "
+                                         f"NCCL max_ctas={os.environ.get('CAVP_NCCL_MAX_CTAS', NCCL_MAX_CTAS_DEFAULT)}")
+                           if world > 1 else None},
                 "clocks": clocks,
                 "e2e": {"value": e2e, "unit": "images/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes,
-                        "d2h_bytes_per_step": 8},
+                        "d2h_bytes_per_step": 8,
+                        "how": "cavp_b200.trainer.train_step from pinned host buffers: H2D of image / audio / labels every "
+                               "step (prefetched on a copy stream), both losses copied D2H every step and read on the host "
+                               "one step later; last losses read: %s" % (readback["last"],)},
                 "gpu_launches": launches_per_step * args.steps,
                 "gpu_launches_per_step": launches_per_step, "host_issue_ms_per_step": host_issue_ms,
                 "roofline": roofline, "attn_roofline": attn_roof, "kernel_ms_top": breakdown,

@@ -453,6 +453,17 @@ static int igemm_row_impl(const float* x, const float* w, const void* w_bf16, fl
   if (slabs && p.splits != splits) return CAVP_ERR_ARG;  // the caller sized y for exactly |splits| slabs
   if (p.splits > 1 && (y_pre || scale || shift || res || stats || act != ACT_NONE)) return CAVP_ERR_ARG;
   fill_divs(p);
+  // Promotion unit of the CTA-pair kernel: 2 k-blocks (64 K-elements, error ~5e-7 for every K).  Short-K linear layers
+  // (the fusion block, K = 304: 10 k-blocks per tile) are bound by their promotion / epilogue warps (ncu: ~90 % busy,
+  // tensor pipe 49 %): they take half of their K extent per unit (<= 6 k-blocks = 192 K-elements, error ~1.5e-6),
+  // which cuts the tcgen05.ld + add work per tile 2.5x.  CAVP_IGEMM_UNIT=2 restores the 64-element units.
+  p.unit_kb = 2;
+  {
+    static const char* unit_env = getenv("CAVP_IGEMM_UNIT");
+    const bool linear = r == 1 && s == 1 && stride == 1 && pad == 0 && hs == ho && ws == wo;
+    if (linear && p.num_kb > 4 && p.num_kb <= 12 && p.splits == 1 && !(unit_env && unit_env[0] == '2'))
+      p.unit_kb = (p.num_kb + 1) / 2;
+  }
   if (b_lo_off > 0 && ((b_lo_off & 3) || (reinterpret_cast<uintptr_t>(w) & 15))) return CAVP_ERR_ALIGN;
   if (use_bf16) {
     // 256-column pair tiles where they pad N no more than 128-column tiles do (N = 256, 512, 1024, 2048 ...)
@@ -514,6 +525,7 @@ static int wgrad_impl(const float* dy, const float* x, float* dw, int nimg, int 
   p.red_len = static_cast<int>(P);
   p.num_kb = (p.red_len + BK - 1) / BK;
   p.splits = splits < 1 ? 1 : (splits > p.num_kb ? p.num_kb : splits);
+  p.unit_kb = 2;
   fill_divs(p);
   return dispatch<MODE_WGRAD>(p, prec, dy_lo_off, static_cast<cudaStream_t>(stream));
 }

@@ -55,6 +55,7 @@ struct IgemmParams {
   int act;
   float slope;
   int n_tiles, num_kb, splits;
+  int unit_kb;         // k-blocks per promotion unit of the CTA-pair kernel (igemm_ws2.cuh); 2 unless set by the dispatcher
   long long split_slab;  // > 0: deterministic split-K - split i stores its partial product at y + i*split_slab (no atomics)
   FastDiv div_howo, div_wo, div_c, div_s;
 };
@@ -127,6 +128,28 @@ __device__ __forceinline__ void store_staged(uint32_t scratch, float* ybase, int
   for (int rr = 0; rr < 8; ++rr) {
     const int r = rr * 4 + rsub;
     const float4 t = lds_v4(scratch + static_cast<uint32_t>((r * EPI_LDS + c4 * 4) * 4));
+    if (row0 + r < M) *reinterpret_cast<float4*>(ybase + static_cast<size_t>(r) * ldy + c4 * 4) = t;
+  }
+}
+// store_staged with the per-column part of the epilogue applied on the way out: each lane owns ONE column quad, so
+// scale / shift are one 16-byte load per lane and chunk instead of 32 scalar loads per thread in the register phase
+__device__ __forceinline__ void store_staged_affine(uint32_t scratch, float* ybase, int ldy, int row0, int M, int lane,
+                                                    const float* scale, const float* shift, int act, float slope) {
+  const int c4 = lane & 7, rsub = lane >> 3;
+  float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (scale) sc = __ldg(reinterpret_cast<const float4*>(scale) + c4);
+  if (shift) sh = __ldg(reinterpret_cast<const float4*>(shift) + c4);
+#pragma unroll
+  for (int rr = 0; rr < 8; ++rr) {
+    const int r = rr * 4 + rsub;
+    float4 t = lds_v4(scratch + static_cast<uint32_t>((r * EPI_LDS + c4 * 4) * 4));
+    t.x = fmaf(t.x, sc.x, sh.x); t.y = fmaf(t.y, sc.y, sh.y); t.z = fmaf(t.z, sc.z, sh.z); t.w = fmaf(t.w, sc.w, sh.w);
+    if (act == ACT_RELU) {
+      t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f);
+    } else if (act == ACT_LEAKY) {
+      t.x = t.x > 0.f ? t.x : t.x * slope; t.y = t.y > 0.f ? t.y : t.y * slope;
+      t.z = t.z > 0.f ? t.z : t.z * slope; t.w = t.w > 0.f ? t.w : t.w * slope;
+    }
     if (row0 + r < M) *reinterpret_cast<float4*>(ybase + static_cast<size_t>(r) * ldy + c4 * 4) = t;
   }
 }
@@ -230,6 +253,17 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmParams& pin, float (&a
           if (j < ncol) f(j);
       }
     };
+    // bias / folded-BN / ReLU only (Linear + bias, eval-mode conv): defer the per-column work to the store phase
+    const bool deferred = full_chunk && (p.scale || p.shift) && !p.res && !p.y_pre && !p.stats &&
+                          (p.act == ACT_NONE || p.act == ACT_RELU || p.act == ACT_LEAKY) &&
+                          (!p.scale || (reinterpret_cast<uintptr_t>(p.scale + col0) & 15) == 0) &&
+                          (!p.shift || (reinterpret_cast<uintptr_t>(p.shift + col0) & 15) == 0);
+    if (deferred) {
+      stage_chunk(scratch, v, lane);
+      store_staged_affine(scratch, p.y + static_cast<size_t>(row0) * p.ldy + col0, p.ldy, row0, p.M, lane,
+                          p.scale ? p.scale + col0 : nullptr, p.shift ? p.shift + col0 : nullptr, p.act, p.slope);
+      continue;
+    }
     if (p.scale) cols([&](int j) { v[j] *= __ldg(p.scale + col0 + j); });
     if (p.shift) cols([&](int j) { v[j] += __ldg(p.shift + col0 + j); });
     if (p.res) {

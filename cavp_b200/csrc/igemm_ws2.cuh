@@ -120,7 +120,7 @@ igemm_ws2_kernel(const IgemmParams p, const __grid_constant__ CUtensorMap tm_b_h
     for (int w = pair_id; w < total_work; w += num_pairs) {
       const Ws2Work wk = ws2_decode(p, w, m_pairs);
       const int m_tile = wk.m_pair * 2 + static_cast<int>(rank);
-      const int nunits = PROMOTE ? ((wk.nkb + 1) >> 1) : 1;
+      const int nunits = PROMOTE ? ((wk.nkb + p.unit_kb - 1) / p.unit_kb) : 1;
       float acc[BN];
 #pragma unroll
       for (int j = 0; j < BN; ++j) acc[j] = 0.f;
@@ -365,13 +365,20 @@ igemm_ws2_kernel(const IgemmParams p, const __grid_constant__ CUtensorMap tm_b_h
       int gbase = 0, ubase = 0;
       for (int w = pair_id; w < total_work; w += num_pairs) {
         const Ws2Work wk = ws2_decode(p, w, m_pairs);
+        // a promotion unit = p.unit_kb k-blocks (2 = 64 K-elements; short-K linear layers use half of their K extent,
+        // see csrc/igemm.cu) accumulated in one TMEM buffer before the promotion warps add it into registers
+        int uin = 0, ucur = 0;  // position inside the unit, unit index inside the tile
         for (int it = 0; it < wk.nkb; ++it) {
           const int G = gbase + it;
           const int s = G % Cfg::STAGES;
-          const int U = ubase + (PROMOTE ? (it >> 1) : 0);
+          const int U = ubase + (PROMOTE ? ucur : 0);
           const int b = U % NBUF;
-          const bool unit_first = PROMOTE ? ((it & 1) == 0) : (it == 0);
-          const bool unit_last = PROMOTE ? ((it & 1) == 1 || it == wk.nkb - 1) : (it == wk.nkb - 1);
+          const bool unit_first = PROMOTE ? (uin == 0) : (it == 0);
+          const bool unit_last = PROMOTE ? (uin == p.unit_kb - 1 || it == wk.nkb - 1) : (it == wk.nkb - 1);
+          if (++uin == p.unit_kb) {
+            uin = 0;
+            ++ucur;
+          }
           if (unit_first) {
             mbar_wait_cluster(&acce_bar[b], (((U / NBUF) & 1) ^ 1));
             tc_fence_after();
@@ -396,7 +403,7 @@ igemm_ws2_kernel(const IgemmParams p, const __grid_constant__ CUtensorMap tm_b_h
           __syncwarp();
         }
         gbase += wk.nkb;
-        ubase += PROMOTE ? ((wk.nkb + 1) >> 1) : 1;
+        ubase += PROMOTE ? ((wk.nkb + p.unit_kb - 1) / p.unit_kb) : 1;
       }
     }
     __syncwarp();

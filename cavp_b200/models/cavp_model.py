@@ -334,6 +334,10 @@ def backbone_forward(g, net, x):
     x = g.maxpool(x, 3, 2, 1)
     feats = []
     for layer in (net.layer1, net.layer2, net.layer3, net.layer4):
+        if layer is net.layer4:
+            # layer4 holds 63 % of the ResNet's parameters and its backward runs first: its gradient bucket is complete
+            # when the tape is back here (cavp_b200/parallel.py:cavp_buckets)
+            g.mark("layer4_grads_done")
         for blk in layer:
             out = g.conv_bn(x, blk.conv1.weight, blk.bn1, **_cv(blk.conv1))
             out = g.conv_bn(out, blk.conv2.weight, blk.bn2, **_cv(blk.conv2))

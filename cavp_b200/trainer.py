@@ -51,9 +51,10 @@ def train_step(model, image, audio, pix_label, shuffle_pix_label, *, temperature
         # data-parallel mode (cavp_b200.parallel): gradients are produced inside the flat buffer and each bucket's
         # all-reduce starts as soon as the backward tape has passed it (DDP-style overlap, main_vpo_mono.py:131-141)
         grad_sink.begin_step()
-        if len(grad_sink.bucket_range) == 3:  # cavp_buckets(): audio | head + fusion | ResNet
-            g.callbacks["audio_grads_done"] = lambda: grad_sink.flush_bucket(0, g.param_grads)
-            g.callbacks["head_grads_done"] = lambda: grad_sink.flush_bucket(1, g.param_grads)
+        from .parallel import BUCKET_MARKERS
+        if len(grad_sink.bucket_range) == len(BUCKET_MARKERS) + 1:  # cavp_buckets(): audio | head | layer4 | rest
+            for b, name in enumerate(BUCKET_MARKERS):
+                g.callbacks[name] = (lambda b=b: grad_sink.flush_bucket(b, g.param_grads))
     g.use_weight_cache(m)
     if labels_dev is None:
         labels_dev = pix_label.to(dev, torch.int64, non_blocking=True)
