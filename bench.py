@@ -552,7 +552,7 @@ def run_ours(args):
                                             "LayerNorm / losses; stems and classifier fp32-grade"}[args.prec],
                            "l2": "working set per step (>10 GB of activations) far exceeds the 126 MB L2; no flush needed",
                            "bn": "local (per-rank) BatchNorm statistics",
-                           "allreduce": (f"4 gradient buckets produced in place, NCCL all-reduce(AVG) of each bucket launched "
+                           "allreduce": (f"5 gradient buckets produced in place, NCCL all-reduce(AVG) of each bucket launched "
                                          f"asynchronously from a backward-tape marker (overlaps the rest of the backward); "
                                          f"NCCL max_ctas={os.environ.get('CAVP_NCCL_MAX_CTAS', NCCL_MAX_CTAS_DEFAULT)}")
                            if world > 1 else None},

@@ -168,19 +168,22 @@ class FlatGradBuffer:
 def cavp_buckets(model):
     """Bucket order = the order in which the backward pass completes them (cavp_b200.models.cavp_model.build_graph
     records the matching tape markers): 0 audio backbone, 1 decoder + fusion + projector + DeepLab head, 2 ResNet layer4,
-    3 the rest of the ResNet (the only bucket whose all-reduce cannot overlap the backward pass: 8.6 M parameters)."""
+    3 layer3, 4 the rest of the ResNet (the only bucket whose all-reduce cannot overlap the backward pass: 1.5 M
+    parameters = 6 MB)."""
     m = model.module if hasattr(model, "module") else model
     audio = list(m.audio_backbone.parameters())
     backbone = list(m.backbone.parameters())
     taken = {id(p) for p in audio + backbone}
     head = [p for p in m.parameters() if id(p) not in taken]
     layer4 = list(m.backbone.backbone.layer4.parameters())
-    l4 = {id(p) for p in layer4}
-    rest = [p for p in backbone if id(p) not in l4]
-    return [audio, head, layer4, rest]
+    layer3 = list(m.backbone.backbone.layer3.parameters())
+    late = {id(p) for p in layer4 + layer3}
+    rest = [p for p in backbone if id(p) not in late]
+    return [audio, head, layer4, layer3, rest]
 
 
-BUCKET_MARKERS = ("audio_grads_done", "head_grads_done", "layer4_grads_done")  # bucket i is complete at marker i
+# bucket i is complete when the backward tape passes marker i (the last bucket: at the end of the backward pass)
+BUCKET_MARKERS = ("audio_grads_done", "head_grads_done", "layer4_grads_done", "layer3_grads_done")
 
 
 def shard_batch(global_batch, rank, world):
