@@ -353,7 +353,9 @@ def run_ours(args):
     from cavp_b200.optim import SGD, Adam
     opt_v = SGD(visual_params, lr=1e-3 * world, momentum=0.9, weight_decay=5e-4)
     opt_a = Adam(audio_params, lr=1e-4 * world)
-    flat = FlatGradBuffer(cavp_buckets(model), dev) if world > 1 else None
+    # gradients live in one flat, bucketed buffer (zeroed by ONE memset per step, written in place by the weight-gradient
+    # kernels); with more than one rank each bucket is all-reduced as soon as the backward pass has completed it
+    flat = FlatGradBuffer(cavp_buckets(model), dev)
 
     image_h, audio_h, pix_h, spl_h = synthetic_batch(B, 666 + rank)
     pinned = [t.pin_memory() for t in (image_h, audio_h, pix_h)]

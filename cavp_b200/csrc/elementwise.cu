@@ -142,49 +142,44 @@ __global__ void gather_rows_kernel(const float* __restrict__ src, const long lon
 // ------------------------------------------------------------------------------------------------ BatchNorm
 // Reduce the per-(m_tile, quarter) partial sums written by the igemm epilogue (fp64 accumulate) and finish the batch
 // statistics.  block = (32 channels, 32 part-lanes): reads are coalesced across channels.
-// stage 1 of the two-stage finalize: block (x = 32 channels, y = slice s of the partial rows) -> one fp64 row
-// ws[s][2][C].  A single block per 32 channels reading 12 K partial rows is bound by one SM's load bandwidth (~20 us
-// per layer at 112x112); sixteen slices per channel group spread the same bytes over 16x more SMs.
-__global__ void bn_partial_reduce_kernel(const float* __restrict__ partials, int nparts, int ldstat, int C,
-                                         double* __restrict__ ws) {
-  __shared__ double sh1[32][33], sh2[32][33];
-  const int ch = blockIdx.x * 32 + threadIdx.x;
-  const int S = gridDim.y, sl = blockIdx.y;
-  const int per = (nparts + S - 1) / S;
-  const int beg = sl * per, end = min(nparts, beg + per);
-  double t1[4] = {0.0, 0.0, 0.0, 0.0}, t2[4] = {0.0, 0.0, 0.0, 0.0};
-  if (ch < C) {
-    int i = beg + threadIdx.y;
-    for (; i + 96 < end; i += 128) {
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float* pp = partials + static_cast<size_t>(i + 32 * u) * 2 * ldstat;
-        t1[u] += pp[ch];
-        t2[u] += pp[ldstat + ch];
-      }
-    }
-    for (; i < end; i += 32) {
-      const float* pp = partials + static_cast<size_t>(i) * 2 * ldstat;
-      t1[0] += pp[ch];
-      t2[0] += pp[ldstat + ch];
-    }
-  }
-  sh1[threadIdx.y][threadIdx.x] = (t1[0] + t1[1]) + (t1[2] + t1[3]);
-  sh2[threadIdx.y][threadIdx.x] = (t2[0] + t2[1]) + (t2[2] + t2[3]);
-  __syncthreads();
-  if (threadIdx.y == 0 && ch < C) {
-    double s1 = 0.0, s2 = 0.0;
-    for (int j = 0; j < 32; ++j) {
-      s1 += sh1[j][threadIdx.x];
-      s2 += sh2[j][threadIdx.x];
-    }
-    ws[(static_cast<size_t>(sl) * 2 + 0) * C + ch] = s1;
-    ws[(static_cast<size_t>(sl) * 2 + 1) * C + ch] = s2;
-  }
-}
-
 __device__ __forceinline__ float tf32_rn_dev(float x) {  // = ptx.cuh:tf32_rn (round to nearest, ties away)
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+}
+
+// one channel: statistics -> mean / invstd / scale / shift, running-stat update (SyncBatchNorm modes: see the header)
+__device__ __forceinline__ void bn_finish_channel(int ch, int C, double s1, double s2, double count,
+                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                  float* __restrict__ running_mean, float* __restrict__ running_var,
+                                                  float momentum, float eps, float* __restrict__ mean_out,
+                                                  float* __restrict__ invstd_out, float* __restrict__ scale_out,
+                                                  float* __restrict__ shift_out, double* __restrict__ sums_io,
+                                                  int sums_mode, long long* __restrict__ num_batches_tracked) {
+  if (sums_mode == 1) {  // only export local sums + the local count (SyncBatchNorm: all-reduced, then mode 2)
+    sums_io[ch] = s1;
+    sums_io[C + ch] = s2;
+    if (ch == 0) sums_io[2 * C] = count;
+    return;
+  }
+  if (sums_mode == 2) {  // global sums and the GLOBAL count come from the all-reduced buffer: no host round trip
+    s1 = sums_io[ch];
+    s2 = sums_io[C + ch];
+    count = sums_io[2 * C];
+  }
+  if (ch == 0 && num_batches_tracked) num_batches_tracked[0] += 1;  // nn.BatchNorm2d bookkeeping, same launch
+  const double mean = s1 / count;
+  double var = s2 / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float invstd = 1.0f / sqrtf(static_cast<float>(var) + eps);
+  const float g = gamma ? gamma[ch] : 1.f, b = beta ? beta[ch] : 0.f;
+  mean_out[ch] = static_cast<float>(mean);
+  invstd_out[ch] = invstd;
+  scale_out[ch] = g * invstd;
+  shift_out[ch] = b - static_cast<float>(mean) * g * invstd;
+  if (running_mean) {
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * static_cast<float>(mean);
+    running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * static_cast<float>(unbiased);
+  }
 }
 
 template <typename PT>
@@ -227,32 +222,75 @@ __global__ void bn_finalize_kernel(const PT* __restrict__ partials, int nparts, 
       s1 += sh1[j][threadIdx.x];
       s2 += sh2[j][threadIdx.x];
     }
-    if (sums_mode == 1) {  // only export local sums + the local count (SyncBatchNorm: all-reduced, then mode 2)
-      sums_io[ch] = s1;
-      sums_io[C + ch] = s2;
-      if (ch == 0) sums_io[2 * C] = count;
-      return;
+    bn_finish_channel(ch, C, s1, s2, count, gamma, beta, running_mean, running_var, momentum, eps, mean_out, invstd_out,
+                      scale_out, shift_out, sums_io, sums_mode, num_batches_tracked);
+  }
+}
+
+// Two-stage finalize in ONE launch: block (x = 32 channels, y = slice) reduces its slice of the partial rows to
+// ws[slice][2][C]; the LAST slice block of a channel group (atomic ticket, counter reset for the next launch) adds the S
+// slice rows in a fixed order and finishes the channels.  Same arithmetic and order as partial_reduce + finalize<double>.
+__global__ void bn_reduce_finalize_kernel(const float* __restrict__ partials, int nparts, int ldstat, int C, double count,
+                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                          float* __restrict__ running_mean, float* __restrict__ running_var,
+                                          float momentum, float eps, float* __restrict__ mean_out,
+                                          float* __restrict__ invstd_out, float* __restrict__ scale_out,
+                                          float* __restrict__ shift_out, double* __restrict__ sums_io, int sums_mode,
+                                          long long* __restrict__ num_batches_tracked, double* __restrict__ ws,
+                                          int* __restrict__ counters) {
+  __shared__ double sh1[32][33], sh2[32][33];
+  __shared__ int is_last;
+  const int ch = blockIdx.x * 32 + threadIdx.x;
+  const int S = gridDim.y, sl = blockIdx.y;
+  const int per = (nparts + S - 1) / S;
+  const int beg = sl * per, end = min(nparts, beg + per);
+  double t1[4] = {0.0, 0.0, 0.0, 0.0}, t2[4] = {0.0, 0.0, 0.0, 0.0};
+  if (ch < C) {
+    int i = beg + threadIdx.y;
+    for (; i + 96 < end; i += 128) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float* pp = partials + static_cast<size_t>(i + 32 * u) * 2 * ldstat;
+        t1[u] += pp[ch];
+        t2[u] += pp[ldstat + ch];
+      }
     }
-    if (sums_mode == 2) {  // global sums and the GLOBAL count come from the all-reduced buffer: no host round trip
-      s1 = sums_io[ch];
-      s2 = sums_io[C + ch];
-      count = sums_io[2 * C];
+    for (; i < end; i += 32) {
+      const float* pp = partials + static_cast<size_t>(i) * 2 * ldstat;
+      t1[0] += pp[ch];
+      t2[0] += pp[ldstat + ch];
     }
-    if (ch == 0 && num_batches_tracked) num_batches_tracked[0] += 1;  // nn.BatchNorm2d bookkeeping, same launch
-    const double mean = s1 / count;
-    double var = s2 / count - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float invstd = 1.0f / sqrtf(static_cast<float>(var) + eps);
-    const float g = gamma ? gamma[ch] : 1.f, b = beta ? beta[ch] : 0.f;
-    mean_out[ch] = static_cast<float>(mean);
-    invstd_out[ch] = invstd;
-    scale_out[ch] = g * invstd;
-    shift_out[ch] = b - static_cast<float>(mean) * g * invstd;
-    if (running_mean) {
-      const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
-      running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * static_cast<float>(mean);
-      running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * static_cast<float>(unbiased);
+  }
+  sh1[threadIdx.y][threadIdx.x] = (t1[0] + t1[1]) + (t1[2] + t1[3]);
+  sh2[threadIdx.y][threadIdx.x] = (t2[0] + t2[1]) + (t2[2] + t2[3]);
+  __syncthreads();
+  if (threadIdx.y == 0 && ch < C) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int j = 0; j < 32; ++j) {
+      s1 += sh1[j][threadIdx.x];
+      s2 += sh2[j][threadIdx.x];
     }
+    ws[(static_cast<size_t>(sl) * 2 + 0) * C + ch] = s1;
+    ws[(static_cast<size_t>(sl) * 2 + 1) * C + ch] = s2;
+    __threadfence();  // this slice row is visible device-wide before the ticket is taken
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    const int ticket = atomicAdd(&counters[blockIdx.x], 1);
+    is_last = ticket == S - 1;
+    if (is_last) counters[blockIdx.x] = 0;  // ready for the next launch (launches of a stream are ordered)
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  if (threadIdx.y == 0 && ch < C) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int j = 0; j < S; ++j) {  // fixed order, whichever block arrives last
+      s1 += __ldcg(ws + (static_cast<size_t>(j) * 2 + 0) * C + ch);
+      s2 += __ldcg(ws + (static_cast<size_t>(j) * 2 + 1) * C + ch);
+    }
+    bn_finish_channel(ch, C, s1, s2, count, gamma, beta, running_mean, running_var, momentum, eps, mean_out, invstd_out,
+                      scale_out, shift_out, sums_io, sums_mode, num_batches_tracked);
   }
 }
 // eval mode: scale/shift from running statistics
@@ -721,18 +759,21 @@ extern "C" int cavp_bn_finalize(const float* partials, int nparts, int ldstat, i
     // two-stage path; the fp64 workspace is per device and reused by every call (launches of one stream are ordered;
     // the engine issues all BatchNorm work on one stream)
     static double* ws_dev[64] = {nullptr};
+    static int* cnt_dev[64] = {nullptr};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) return CAVP_ERR_ARG;
     if (!ws_dev[dev]) {
       cudaError_t e = cudaMalloc(&ws_dev[dev], sizeof(double) * S * 2 * WS_C);
       if (e != cudaSuccess) return static_cast<int>(e);
+      e = cudaMalloc(&cnt_dev[dev], sizeof(int) * (WS_C / 32));
+      if (e != cudaSuccess) return static_cast<int>(e);
+      e = cudaMemset(cnt_dev[dev], 0, sizeof(int) * (WS_C / 32));  // once; the kernel leaves the tickets at zero
+      if (e != cudaSuccess) return static_cast<int>(e);
     }
-    bn_partial_reduce_kernel<<<dim3((C + 31) / 32, S), dim3(32, 32), 0, ST(stream)>>>(partials, nparts, ldstat, C,
-                                                                                    ws_dev[dev]);
-    bn_finalize_kernel<double><<<(C + 31) / 32, dim3(32, 32), 0, ST(stream)>>>(
-        ws_dev[dev], S, C, C, count, gamma, beta, running_mean, running_var, momentum, eps, mean_out, invstd_out,
-        scale_out, shift_out, sums_io, sums_mode, num_batches_tracked);
+    bn_reduce_finalize_kernel<<<dim3((C + 31) / 32, S), dim3(32, 32), 0, ST(stream)>>>(
+        partials, nparts, ldstat, C, count, gamma, beta, running_mean, running_var, momentum, eps, mean_out, invstd_out,
+        scale_out, shift_out, sums_io, sums_mode, num_batches_tracked, ws_dev[dev], cnt_dev[dev]);
     CAVP_LAUNCH_CHECK();
   }
   bn_finalize_kernel<float><<<(C + 31) / 32, dim3(32, 32), 0, ST(stream)>>>(

@@ -313,6 +313,7 @@ class Graph:
         self.device = device
         # grad_sink: a cavp_b200.parallel.FlatGradBuffer - weight-gradient kernels write straight into its views
         self.grad_sink = grad_sink
+        self._dw_prezeroed = False
         self.callbacks = {}  # name -> callable, fired by the matching tape marker during backward()
         self.prec = prec  # 2 = fp32 parity (3xTF32 + promotion), 1 = plain TF32, 3 = bf16 operands (configs[2])
         # bf16 mode: forward / dgrad GEMMs outside the bf16 kernel's envelope (3/4-channel stems, the padded classifier,
@@ -439,7 +440,9 @@ class Graph:
                 and id(wr.param) not in self.param_grads):
             v = sink.view_of(wr.param)
             if v is not None:
+                self._dw_prezeroed = bool(getattr(sink, "prezeroed", False))
                 return (v if wr.kind == "linear" else v.permute(0, 2, 3, 1)).reshape(co, K)
+        self._dw_prezeroed = False
         return self.empty(co, K)
 
     def add_param_grad(self, p, g):
@@ -685,7 +688,7 @@ class Graph:
                 if wr.param.requires_grad:
                     dwk = self.weight_grad_buffer(wr, co, K)
                     wsplits = self.wgrad_splits(M, co, K)
-                    if wsplits > 1:
+                    if wsplits > 1 and not self._dw_prezeroed:  # (the flat gradient buffer is zeroed once per step)
                         self.call("cavp_zero", dwk.data_ptr(), dwk.numel() * 4)
                     if self.wgrad_bf16_ok(x.c, co):
                         g16 = g.split if (g is dy and g.split is not None and g.split.dtype == torch.bfloat16) else None

@@ -39,7 +39,7 @@ class FlatGradBuffer:
         self.views = [self._make_view(i) for i in range(len(self.params))]
         self.used = [False] * len(self.params)
         self._pending = []
-        self._copy_cache = None
+        self.prezeroed = False  # True between begin_step() and the end of the step: the views hold zeros
 
     def _make_view(self, i):
         p = self.params[i]
@@ -74,9 +74,9 @@ class FlatGradBuffer:
             g = grads.get(id(p))
             v = self.views[i]
             if g is None:
-                if self.used[i]:
+                if self.used[i] and not self.prezeroed:
                     v.zero_()
-                    self.used[i] = False
+                self.used[i] = False
                 continue
             if g.data_ptr() != v.data_ptr():
                 todo.append((i, g))
@@ -126,7 +126,15 @@ class FlatGradBuffer:
         self._pending.append((b, work, scale))
 
     def begin_step(self):
+        """Start of a step: ONE memset of the whole buffer, so that split-K weight gradients (red.global.add into their
+        view) need no per-layer zeroing and parameters without a gradient contribute zeros to the collective."""
         self._flushed = set()
+        if self.flat.is_cuda:
+            _C.call("cavp_zero", self.flat.data_ptr(), self.flat.numel() * 4,
+                    torch.cuda.current_stream(self.flat.device).cuda_stream)
+        else:
+            self.flat.zero_()
+        self.prezeroed = True
 
     def flush_bucket(self, b, grads, group=None, average=True):
         """Bucket b is complete (the backward tape passed its marker): pack what was not produced in place and start

@@ -109,6 +109,7 @@ def train_step(model, image, audio, pix_label, shuffle_pix_label, *, temperature
     g.backward()
     if grad_sink is not None:
         grad_sink.finish(g.param_grads)  # p.grad = views of the (averaged) flat buffer
+        grad_sink.prezeroed = False
     elif assign_grads:
         for p in m.parameters():
             gr = g.param_grads.get(id(p))
