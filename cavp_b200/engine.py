@@ -7,6 +7,8 @@ streams.  Gradient fan-in is resolved inside kernels (igemm residual epilogue / 
 Activations are `Act`s: NHWC fp32 storage `[n*h*w, ld]` with a channel window `[off, off+c)`, so concat buffers and
 their slices need no copies.  Token tensors `[rows, N, C]` are the same thing with (h, w) = token grid.
 """
+import os
+
 import torch
 
 from . import _C
@@ -529,7 +531,6 @@ class Graph:
         bn = 128 if K > 64 else 64
         tiles = ((cout + 127) // 128) * ((K + bn - 1) // bn)
         num_kb = (P + 31) // 32
-        import os
         overhead = int(os.environ.get("CAVP_WGRAD_OVERHEAD", "12"))
         best, best_cost = 1, None
         for s in range(1, max(1, min(num_kb // 4, 96)) + 1):
@@ -541,14 +542,12 @@ class Graph:
 
     def wgrad_bf16_ok(self, cin, cout):
         """bf16 row: weight gradients with bf16 operands (csrc/igemm_wgrad_bf16.cuh) inside that kernel's envelope."""
-        import os
         return (self.prec == 3 and cin % 8 == 0 and cout % 8 == 0 and cout > 128
                 and os.environ.get("CAVP_WGRAD_BF16", "1") != "0")
 
     @staticmethod
     def wgrad_via_tma(P, cout, K):
         """The split pass over dY costs 12 B per element; it pays when enough column tiles (K / 128) re-read dY."""
-        import os
         forced = os.environ.get("CAVP_WGRAD_TMA")
         if forced is not None:
             return forced != "0"

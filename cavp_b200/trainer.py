@@ -70,7 +70,6 @@ def train_step(model, image, audio, pix_label, shuffle_pix_label, *, temperature
         half, pix, labels = sel
         gpix = (pix + half * (B * fusion.h * fusion.w)).pin_memory().to(dev, non_blocking=True)
         labels_sel = labels.pin_memory().to(dev, non_blocking=True)
-    rows = fusion.n
     # forward_cls + CrossEntropyLoss.  CE on output_cat[:B] + output_cat[B:]*0.0 == CE on the first B images (value
     # and gradient).  Callers that want the full-resolution prediction back (keep_outputs) get it materialised for all
     # rows, as the reference returns it (cavp_model.py:138-141); otherwise the upsample is fused into the loss kernels
