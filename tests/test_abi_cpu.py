@@ -136,3 +136,16 @@ def test_wgrad_split_heuristic_avoids_wave_spill():
         assert ctas > (waves - 1) * NUM_SMS + NUM_SMS // 3 or waves == 1, (P, cout, K, s, ctas)
     assert Graph.wgrad_via_tma(200704, 256, 2736) and Graph.wgrad_via_tma(25088, 2048, 512)
     assert not Graph.wgrad_via_tma(200704, 1216, 304) and not Graph.wgrad_via_tma(401408, 16, 4096)
+
+
+def test_integration_md_ctypes_stub_matches_the_header():
+    """INTEGRATION.md section 4 shows a reference-side ctypes stub for cavp_igemm; its argtypes must be the header's."""
+    import ctypes
+    import re
+    from cavp_b200 import _C
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    m = re.search(r"lib\.cavp_igemm\.argtypes = (.+?)\s+#", text)
+    assert m, "the stub moved: update this test"
+    ns = {"P": ctypes.c_void_p, "I": ctypes.c_int, "F": ctypes.c_float, "LL": ctypes.c_longlong}
+    stub = eval(m.group(1), {"__builtins__": {}}, ns)
+    assert stub == _C.parse_header()["cavp_igemm"]
