@@ -104,6 +104,7 @@ class InfoNCE:
         wsplits = Graph.wgrad_splits(A, A4, C)
         if wsplits > 1:
             g.call("cavp_zero", d2.data_ptr(), d2.numel() * 4)
+        g.work(flops=2.0 * A * A4 * C, tag=f"wgrad P{A} Cout{A4} K{C} (InfoNCE G^T A) splits{wsplits}")
         g.call("cavp_igemm_wgrad", G.data_ptr(), self.anchors.data_ptr(), d2.data_ptr(), A, 1, 1, C, C, 1, 1, 1, 1, 1, 0,
                1, A4, A4, wsplits, g.prec_tf)
         g.call("cavp_add_inplace", d1.data_ptr(), d2.data_ptr(), A * C, 1.0)
