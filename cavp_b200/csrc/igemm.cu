@@ -8,6 +8,7 @@
 #include "igemm_bf16.cuh"
 #include "igemm_ws2x.cuh"
 #include "igemm_wgrad_bf16.cuh"
+#include "igemm_lin.cuh"
 #include <cuda_bf16.h>
 #include "../../include/cavp_b200.h"
 
@@ -158,6 +159,36 @@ static int launch_igemm_ws2x(const IgemmParams& p, const CUtensorMap& tm_hi, con
   return static_cast<int>(cudaGetLastError());
 }
 
+// short-K linear layers: 8 promotion / epilogue warps + 8 producer warps (igemm_lin.cuh)
+template <int BN>
+static int launch_igemm_lin(const IgemmParams& p, const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, cudaStream_t st) {
+  using Cfg = LinCfg<BN>;
+  auto kern = igemm_lin_kernel<BN>;
+  static int max_pairs_dev[MAX_DEVICES] = {};
+  int& max_pairs = max_pairs_dev[current_device()];
+  if (max_pairs == 0) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(148, 1, 1);
+    cfg.blockDim = dim3(LIN_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    int n = 0;
+    e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+    if (e != cudaSuccess || n < 1) {
+      cudaGetLastError();
+      n = 74;
+    }
+    max_pairs = n;
+  }
+  const int m_tiles = (p.M + BM - 1) / BM;
+  const int m_pairs = (m_tiles + 1) / 2;
+  const int total_work = m_pairs * p.n_tiles;
+  const int pairs = total_work < max_pairs ? total_work : max_pairs;
+  kern<<<2 * pairs, LIN_THREADS, Cfg::SMEM_BYTES, st>>>(p, tm_hi, tm_lo, total_work, m_pairs);
+  return static_cast<int>(cudaGetLastError());
+}
+
 template <int PREC>
 static int launch_wgrad2(const IgemmParams& p, const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, cudaStream_t st) {
   using Cfg = Wg2Cfg<PREC>;
@@ -267,6 +298,24 @@ static int dispatch(IgemmParams& p, int prec, long long b_lo_off, cudaStream_t s
           rc = make_weight_tmap(&tm_lo, p.w + b_lo_off, p.Ncols, p.K, p.ldw, 128);
           if (rc) return rc;
           return launch_igemm_ws2x(p, tm_hi, tm_lo, st);
+        }
+      }
+      {
+        // short-K linear layers (the fusion block): the schedule with eight promotion / epilogue warps
+        static const char* lin_env = getenv("CAVP_IGEMM_LIN");
+        const bool linear = p.R == 1 && p.S == 1 && p.stride == 1 && p.pad == 0 && p.Hs == p.Ho && p.Ws == p.Wo;
+        const bool lin_ok = sched == 2 && bn == 128 && prec == 2 && linear && (p.num_kb & 1) == 0 && p.num_kb <= 40 &&
+                            lin_epilogue_ok(p) && !(lin_env && lin_env[0] == '0');
+        if (lin_ok) {
+          const int pad128 = (p.Ncols + 127) / 128 * 128, pad160 = (p.Ncols + 159) / 160 * 160;
+          const bool bn160 = pad160 <= pad128;
+          const int pbn = bn160 ? 160 : 128;
+          p.n_tiles = (p.Ncols + pbn - 1) / pbn;
+          rc = make_weight_tmap(&tm_hi, p.w, p.Ncols, p.K, p.ldw, pbn / 2);
+          if (rc) return rc;
+          rc = make_weight_tmap(&tm_lo, p.w + b_lo_off, p.Ncols, p.K, p.ldw, pbn / 2);
+          if (rc) return rc;
+          return bn160 ? launch_igemm_lin<160>(p, tm_hi, tm_lo, st) : launch_igemm_lin<128>(p, tm_hi, tm_lo, st);
         }
       }
       if (sched == 2 && bn == 128) {  // CTA-pair kernel: each CTA fetches half of the weight rows

@@ -18,6 +18,7 @@ FORCED = [
     {"CAVP_IGEMM_WS": "2", "CAVP_IGEMM_BN160": "1"},          # CTA pair, 160-column tiles
     {"CAVP_IGEMM_WS": "2", "CAVP_IGEMM_BN256": "1"},          # CTA pair, 256-column tiles wherever N % 256 == 0
     {"CAVP_IGEMM_BN256": "0"},                                # never the 256-column kernel
+    {"CAVP_IGEMM_WS": "2", "CAVP_IGEMM_LIN": "0"},            # linear layers on the generic pair kernel's fast path
     {"CAVP_WGRAD_TMA": "1", "CAVP_WGRAD_PAIR": "1"},          # every weight gradient through the TMA + pair kernel
     {"CAVP_WGRAD_TMA": "1", "CAVP_WGRAD_PAIR": "0"},          # TMA-fed single-CTA weight gradient
     {"CAVP_WGRAD_TMA": "0"},                                  # thread-gathered weight gradient
