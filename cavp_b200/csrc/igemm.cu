@@ -285,6 +285,28 @@ static int dispatch(IgemmParams& p, int prec, long long b_lo_off, cudaStream_t s
       const int pair_items = ((m_tiles_ + 1) / 2) * ((p.Ncols + 127) / 128) * p.splits;
       int sched = prec == 1 ? 1 : (heavy_epilogue ? 0 : ((bn == 128 && m_tiles_ >= 2 && pair_items >= 148) ? 2 : 1));
       if (ws_env) sched = ws_env[0] - '0';
+      {
+        // short-K linear layers (the fusion block): the schedule with eight promotion / epilogue warps
+        static const char* lin_env = getenv("CAVP_IGEMM_LIN");
+        const bool linear = p.R == 1 && p.S == 1 && p.stride == 1 && p.pad == 0 && p.Hs == p.Ho && p.Ws == p.Wo;
+        // layers the 256-column kernel could take as well (N % 256 == 0) go there unless K is short (<= LIN_X_KB k-blocks)
+        static const char* linx_env = getenv("CAVP_IGEMM_LIN_X_KB");
+        const int lin_x_kb = linx_env ? atoi(linx_env) : 0;
+        const bool x_ok = ws2x_epilogue_ok(p);
+        const bool lin_ok = sched == 2 && bn == 128 && prec == 2 && linear && (p.num_kb & 1) == 0 && p.num_kb <= 40 &&
+                            lin_epilogue_ok(p) && !(lin_env && lin_env[0] == '0') && (!x_ok || p.num_kb <= lin_x_kb);
+        if (lin_ok) {
+          const int pad128 = (p.Ncols + 127) / 128 * 128, pad160 = (p.Ncols + 159) / 160 * 160;
+          const bool bn160 = pad160 <= pad128;
+          const int pbn = bn160 ? 160 : 128;
+          p.n_tiles = (p.Ncols + pbn - 1) / pbn;
+          rc = make_weight_tmap(&tm_hi, p.w, p.Ncols, p.K, p.ldw, pbn / 2);
+          if (rc) return rc;
+          rc = make_weight_tmap(&tm_lo, p.w + b_lo_off, p.Ncols, p.K, p.ldw, pbn / 2);
+          if (rc) return rc;
+          return bn160 ? launch_igemm_lin<160>(p, tm_hi, tm_lo, st) : launch_igemm_lin<128>(p, tm_hi, tm_lo, st);
+        }
+      }
       if (sched == 2 && bn == 128 && prec == 2 && ws2x_epilogue_ok(p)) {
         // 256-column pair tiles (igemm_ws2x.cuh) when the halved number of work items still fills the 74 TPCs evenly
         static const char* x_env = getenv("CAVP_IGEMM_BN256");
@@ -298,24 +320,6 @@ static int dispatch(IgemmParams& p, int prec, long long b_lo_off, cudaStream_t s
           rc = make_weight_tmap(&tm_lo, p.w + b_lo_off, p.Ncols, p.K, p.ldw, 128);
           if (rc) return rc;
           return launch_igemm_ws2x(p, tm_hi, tm_lo, st);
-        }
-      }
-      {
-        // short-K linear layers (the fusion block): the schedule with eight promotion / epilogue warps
-        static const char* lin_env = getenv("CAVP_IGEMM_LIN");
-        const bool linear = p.R == 1 && p.S == 1 && p.stride == 1 && p.pad == 0 && p.Hs == p.Ho && p.Ws == p.Wo;
-        const bool lin_ok = sched == 2 && bn == 128 && prec == 2 && linear && (p.num_kb & 1) == 0 && p.num_kb <= 40 &&
-                            lin_epilogue_ok(p) && !(lin_env && lin_env[0] == '0');
-        if (lin_ok) {
-          const int pad128 = (p.Ncols + 127) / 128 * 128, pad160 = (p.Ncols + 159) / 160 * 160;
-          const bool bn160 = pad160 <= pad128;
-          const int pbn = bn160 ? 160 : 128;
-          p.n_tiles = (p.Ncols + pbn - 1) / pbn;
-          rc = make_weight_tmap(&tm_hi, p.w, p.Ncols, p.K, p.ldw, pbn / 2);
-          if (rc) return rc;
-          rc = make_weight_tmap(&tm_lo, p.w + b_lo_off, p.Ncols, p.K, p.ldw, pbn / 2);
-          if (rc) return rc;
-          return bn160 ? launch_igemm_lin<160>(p, tm_hi, tm_lo, st) : launch_igemm_lin<128>(p, tm_hi, tm_lo, st);
         }
       }
       if (sched == 2 && bn == 128) {  // CTA-pair kernel: each CTA fetches half of the weight rows

@@ -11,8 +11,8 @@
 // launched with 640 x 96 registers, and 256 x 120 + 256 x 96 + 128 x 40 stays inside that allocation).
 //
 // Tiles are 256 rows x BN columns per CTA pair (BN = 128 or 160: 160 for N = 304 / 1216); the epilogue is the 16-column
-// chunk epilogue of igemm_ws2x.cuh without the BatchNorm partials (bias / folded BN / ReLU / LeakyReLU / in-place
-// accumulate; column tails in multiples of 16).  Launches that need anything else stay on igemm_ws2_kernel.
+// chunk epilogue of igemm_ws2x.cuh (bias / folded BN / ReLU / LeakyReLU in the store phase, or BatchNorm partials of a raw
+// conv output, or in-place accumulate; column tails in multiples of 16).  Launches that need anything else stay on igemm_ws2_kernel.
 #pragma once
 #include "igemm_ws2x.cuh"
 
@@ -47,15 +47,14 @@ struct LinCfg {
 __host__ __device__ __forceinline__ bool lin_epilogue_ok(const IgemmParams& p) {
   const bool plain_res = p.res == nullptr || igemm_inplace_acc(p);
   return plain_res && p.y_pre == nullptr && (p.act == ACT_NONE || p.act == ACT_RELU || p.act == ACT_LEAKY) &&
-         p.stats == nullptr && (p.Ncols % 16) == 0 && (p.ldy & 3) == 0 &&
-         (reinterpret_cast<uintptr_t>(p.y) & 15) == 0 && p.splits == 1;
+         (p.stats == nullptr || (p.scale == nullptr && p.shift == nullptr && p.act == ACT_NONE)) &&
+         (p.Ncols % 16) == 0 && (p.ldy & 3) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 15) == 0 && p.splits == 1;
 }
 
 // ws2x_epilogue generalised to HC columns per thread with a column tail (whole 16-column chunks)
 template <int HC>
 __device__ __forceinline__ void lin_epilogue(const IgemmParams& p, float (&acc)[HC], int m0, int n0, int m_tile, int q,
                                              int lane, uint32_t scratch) {
-  (void)m_tile;
   if (m0 >= p.M) return;
   const int row0 = m0 + q * 32;
   const bool accumulate = igemm_inplace_acc(p);
@@ -97,6 +96,28 @@ __device__ __forceinline__ void lin_epilogue(const IgemmParams& p, float (&acc)[
           }
           *reinterpret_cast<float4*>(dst) = t;
         }
+      }
+    }
+    if (p.stats && !accumulate) {
+      // BatchNorm partials of a train-mode conv (no per-column work in that case: the staged values are final):
+      // lane = (row half, column), 16 rows each, then one shuffle - as in ws2x_epilogue
+      const int col = lane & 15, hf = lane >> 4;
+      const int nrow = p.M - row0 < 32 ? p.M - row0 : 32;
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll 4
+      for (int r = hf * 16; r < hf * 16 + 16; ++r) {
+        if (r < nrow) {
+          const float t = lds_f32(scratch + static_cast<uint32_t>((r * WX_LDS + col) * 4));
+          s1 += t;
+          s2 = fmaf(t, t, s2);
+        }
+      }
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+      if (hf == 0) {
+        float* st = p.stats + static_cast<size_t>(m_tile * 4 + q) * 2 * p.ldstat;
+        st[col0 + col] = s1;
+        st[p.ldstat + col0 + col] = s2;
       }
     }
   }
