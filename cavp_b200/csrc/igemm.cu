@@ -276,14 +276,15 @@ static int dispatch(IgemmParams& p, int prec, long long b_lo_off, cudaStream_t s
       // Schedule choice, measured per shape at PREC=2 (profiles/r01_shape_sweep_sched.txt):
       //  * the persistent kernel (ws) beats the one-tile-per-CTA kernel by 5-30 % (its epilogue overlaps the next tile's
       //    main loop; short-K GEMMs gain most) except when the epilogue fetches a residual or evaluates erf/exp;
-      //  * the CTA-pair kernel (ws2) adds 5-15 % on top when there are enough 256-row pair tiles to keep all 74 TPCs
-      //    busy (each SM reads only half of the weight tile from shared memory); with 160-column tiles where they pad N
+      //  * the CTA-pair kernel (ws2) adds 5-15 % on top when there are enough 256-row pair tiles to give every one of the
+      //    74 TPCs an item (each SM reads only half of the weight tile from shared memory; round 2: the VGG 512-channel
+      //    convs, M = 6144, went from 228 to 303 TFLOP/s when the threshold dropped from two waves to one); with 160-column tiles where they pad N
       //    less than 128-column tiles (N = 304: +35 %) or barely more on long-K GEMMs (N = 2048, K >= 1024: +13 %).
       // CAVP_IGEMM_WS=0/1/2 forces tile / ws / pair.
       const int m_tiles_ = (p.M + BM - 1) / BM;
       const bool heavy_epilogue = (p.res != nullptr && !igemm_inplace_acc(p)) || p.act == ACT_GELU || p.act == ACT_SIGMOID;
       const int pair_items = ((m_tiles_ + 1) / 2) * ((p.Ncols + 127) / 128) * p.splits;
-      int sched = prec == 1 ? 1 : (heavy_epilogue ? 0 : ((bn == 128 && m_tiles_ >= 2 && pair_items >= 148) ? 2 : 1));
+      int sched = prec == 1 ? 1 : (heavy_epilogue ? 0 : ((bn == 128 && m_tiles_ >= 2 && pair_items >= 74) ? 2 : 1));
       if (ws_env) sched = ws_env[0] - '0';
       {
         // short-K linear layers (the fusion block): the schedule with eight promotion / epilogue warps

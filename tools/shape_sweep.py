@@ -40,6 +40,11 @@ CASES = [
     ("l4 3x3 fwd d2     M25088 N512 K4608 ", "row", 32, 28, 512, 512, 3, 1, 2, 2, dict(stats=1)),
     ("l3 1x1 fwd stats  M25088 N1024 K256 ", "row", 32, 28, 256, 1024, 1, 1, 0, 1, dict(stats=1)),
     ("l3 3x3 fwd d1     M25088 N256 K2304 ", "row", 32, 28, 256, 256, 3, 1, 1, 1, dict(stats=1)),
+    ("l2 3x3 fwd stats  M25088 N128 K1152 ", "row", 32, 28, 128, 128, 3, 1, 1, 1, dict(stats=1)),
+    ("l2 1x1 fwd stats  M25088 N128 K512  ", "row", 32, 28, 512, 128, 1, 1, 0, 1, dict(stats=1)),
+    ("l2 1x1 dgrad      M25088 N512 K128  ", "row", 32, 28, 128, 512, 1, 1, 0, 1, dict(dgrad=1)),
+    ("vgg c3 fwd relu   M24576 N256 K2304 ", "row", 64, 24, 256, 256, 3, 1, 1, 1, dict(shift=1, act=1)),
+    ("vgg c5 fwd relu   M6144 N512 K4608  ", "row", 64, 12, 512, 512, 3, 1, 1, 1, dict(shift=1, act=1)),
     ("l1 1x1 fwd stats  M100352 N256 K64  ", "row", 32, 56, 64, 256, 1, 1, 0, 1, dict(stats=1)),
     ("l1 3x3 fwd stats  M100352 N64 K576  ", "row", 32, 56, 64, 64, 3, 1, 1, 1, dict(stats=1)),
     ("stem3 fwd stats   M401408 N128 K576 ", "row", 32, 112, 64, 128, 3, 1, 1, 1, dict(stats=1)),
