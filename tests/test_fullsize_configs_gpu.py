@@ -1,5 +1,6 @@
 """BASELINE.json configs[2..4] at FULL size on one B200 (per-GPU shard of each config): one train step through the C-ABI
-kernels, checked through properties that do not need a CPU oracle at that size:
+kernels, checked through size-independent properties (the element-wise comparison of the same steps with the fp64 oracle
+on the GPU lives in tests/test_parity_fullsize_oracle_gpu.py):
 
   * losses and every gradient finite, logits not degenerate;
   * the CE kernel agrees with torch's cross_entropy evaluated on the RETURNED full-resolution logits (an independent
