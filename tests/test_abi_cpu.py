@@ -149,3 +149,36 @@ def test_integration_md_ctypes_stub_matches_the_header():
     ns = {"P": ctypes.c_void_p, "I": ctypes.c_int, "F": ctypes.c_float, "LL": ctypes.c_longlong}
     stub = eval(m.group(1), {"__builtins__": {}}, ns)
     assert stub == _C.parse_header()["cavp_igemm"]
+
+
+def test_gradient_buckets_partition_the_model_in_backward_completion_order():
+    """cavp_b200.parallel.cavp_buckets: every trainable parameter in exactly one bucket; bucket order = the order in
+    which the backward tape completes them (audio, head + fusion, layer4, layer3, rest of the ResNet); one marker per
+    bucket except the last."""
+    from cavp_b200.models.cavp_model import CAVP
+    from cavp_b200.parallel import BUCKET_MARKERS, FlatGradBuffer, cavp_buckets
+    args = SimpleNamespace(seg_model="DeepLabV3Plus", last_three_dilation_stride=[False, True, True],
+                           audio_backbone="vgg", num_classes=22, batch_size=2, local_rank="cpu")
+    m = CAVP(50, None, num_classes=22, args=args, in_plane=1)
+    buckets = cavp_buckets(m)
+    assert len(buckets) == len(BUCKET_MARKERS) + 1 == 5
+    ids = [id(p) for b in buckets for p in b]
+    assert len(ids) == len(set(ids)) == len(list(m.parameters()))
+    assert {id(p) for p in buckets[0]} == {id(p) for p in m.audio_backbone.parameters()}
+    assert {id(p) for p in buckets[2]} == {id(p) for p in m.backbone.backbone.layer4.parameters()}
+    names = {id(p): n for n, p in m.named_parameters()}
+    assert all(names[i].startswith("backbone.") for i in map(id, buckets[4]))
+    assert not any(names[i].startswith(("backbone.", "audio_backbone.")) for i in map(id, buckets[1]))
+    flat = FlatGradBuffer(buckets, "cpu")
+    assert [lo for lo, _ in flat.bucket_range] == sorted(lo for lo, _ in flat.bucket_range)
+    sizes = [hi - lo for lo, hi in flat.bucket_range]
+    assert sizes[0] > 0.6 * sum(sizes) and sizes[4] < 0.02 * sum(sizes)  # audio = 63 % of the bytes, the tail 1.3 %
+
+
+def test_forward_split_k_rule_for_long_k_256_column_layers():
+    from cavp_b200.engine import Graph
+    assert Graph.fwd_splits(25088, 256, 18432) == 2      # ASPP 3x3: 98 pair tiles of 256 columns -> 196 work items
+    assert Graph.fwd_splits(25088, 2048, 2304) == 1      # 784 items: fills the 74 CTA pairs without a split
+    assert Graph.fwd_splits(200704, 256, 2304) == 1
+    assert Graph.fwd_splits(25088, 256, 2304) == 1       # K too short for a split to pay
+    assert Graph.fwd_splits(64, 4096, 12288) > 1         # VGG fc: weight-bandwidth bound, deterministic slabs
