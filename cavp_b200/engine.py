@@ -600,8 +600,12 @@ class Graph:
             else:
                 stats = stats_buf  # (tensor [nparts, 2, ldstat], pointer offset to our columns, nparts, ldstat)
                 assert stats[2] == nparts
+        # A conv whose output feeds a BatchNorm (want_stats) gets d(y) from bn_bwd_apply, which can emit the TF32 split /
+        # bf16 copy on its way out: the TMA-fed weight-gradient kernels then cost no extra pass, so they are used from
+        # K >= 256 when CAVP_WGRAD_FREE_SPLIT=1 (experimental; default: only where the split pass would pay for itself)
+        free_split = want_stats and os.environ.get("CAVP_WGRAD_FREE_SPLIT", "0") != "0" and co >= 64 and K >= 256
         if self.train and wr.param.requires_grad and y.off == 0 and y.ld == co and (
-                self.wgrad_bf16_ok(x.c, co) or self.wgrad_via_tma(M, co, K)):
+                self.wgrad_bf16_ok(x.c, co) or self.wgrad_via_tma(M, co, K) or free_split):
             # BatchNorm's backward then emits d(y) together with its TF32 split / bf16 copy
             y.want_split = "bf16" if self.wgrad_bf16_ok(x.c, co) else "tf32"
         splits = self.fwd_splits(M, co, K)
@@ -698,7 +702,8 @@ class Graph:
                                   tag=f"wgrad(bf16) P{M} Cout{co} K{K} k{r} s{stride} d{dil} splits{wsplits}")
                         self.call("cavp_igemm_wgrad_bf16", g16.data_ptr(), x.ptr, dwk.data_ptr(), x.n, x.h, x.w, x.c,
                                   x.ld, ho, wo, r, s, stride, pad, dil, co, wsplits)
-                    elif self.wgrad_via_tma(M, co, K):
+                    elif self.wgrad_via_tma(M, co, K) or (g is dy and g.split is not None
+                                                          and g.split.dtype == torch.float32):
                         # dY pre-split once (dense hi | lo) and fetched by TMA by every one of the K/128 column tiles
                         gsp = g.split if (g is dy and g.split is not None and g.split.dtype == torch.float32) else None
                         if gsp is None:
