@@ -450,12 +450,19 @@ def run_ours(args):
     # allocator priming (part of set-up, like building the model): the first steps of a process still grow the caching
     # allocator's pools (~12 GB of activations per step) with synchronous cudaMallocs; the W warm-up steps then run in
     # the steady state every later step of a training job sees
-    for _ in range(3):
+    for i in range(3):
         step(True)
+        if args.mem_trace:
+            torch.cuda.synchronize()
+            print(f"[mem] after set-up step {i}: {torch.cuda.memory_allocated(dev) / 2 ** 30:.2f} GiB live, "
+                  f"{torch.cuda.max_memory_allocated(dev) / 2 ** 30:.2f} GiB peak, "
+                  f"{torch.cuda.memory_reserved(dev) / 2 ** 30:.2f} GiB reserved", file=sys.stderr, flush=True)
     torch.cuda.synchronize()
+    torch.cuda.reset_peak_memory_stats(dev)
     ms_res, clocks, launches_per_step = timed(True)
     host_issue_ms = host_ms[0]
     ms_e2e, clocks_e2e, _ = timed(False)
+    hbm_peak_gib = torch.cuda.max_memory_allocated(dev) / 2 ** 30  # live tensors at the peak of a train step
     value = world * B / (ms_res / 1e3)
     e2e = world * B / (ms_e2e / 1e3)
 
@@ -566,6 +573,7 @@ def run_ours(args):
                                "one step later; last losses read: %s" % (readback["last"],)},
                 "gpu_launches": launches_per_step * args.steps,
                 "gpu_launches_per_step": launches_per_step, "host_issue_ms_per_step": host_issue_ms,
+                "hbm_peak_alloc_gib": round(hbm_peak_gib, 2),
                 "roofline": roofline, "attn_roofline": attn_roof, "kernel_ms_top": breakdown,
                 "reference_equiv_tflops": value * FLOPS_PER_IMAGE / 1e12, "cpu_baseline": cpu,
                 "gpu_stock_baseline": stock}
@@ -588,6 +596,7 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=None,
                     help="images per CPU reference step (default: 32 for --impl reference, 8 for the inline cpu_baseline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mem-trace", action="store_true", help="print live / peak / reserved device memory after each set-up step")
     ap.add_argument("--no-stock-baseline", action="store_true",
                     help="skip the stock-PyTorch-on-this-GPU arm (gpu_stock_baseline) and the TF32 peak measurement")
     ap.add_argument("--dump-profile", default=None, help="write the per-launch CUDA-event profile of one step here")

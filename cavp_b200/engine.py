@@ -1040,6 +1040,8 @@ class Graph:
 
     # ------------------------------------------------------------------ backward driver
     def backward(self):
-        for fn in reversed(self.tape):
-            fn()
-        self.tape = []
+        # each closure is dropped as soon as it has run, so the activations and gradients only it still references go
+        # back to the allocator during the backward pass instead of at its end
+        tape = self.tape
+        while tape:
+            tape.pop()()
