@@ -342,6 +342,9 @@ def run_ours(args):
     torch.manual_seed(666 + rank)  # main_*.py: seed_it(seed + local_rank), seed 666
     model = CAVP(50, None, num_classes=CFG["nc"], ignore_index=255, audio_backbone_pretrain_path=None,
                  visual_backbone=50, args=make_args(B, local_rank, args.prec), in_plane=CFG["in_plane"]).to(dev).train()
+    sync_bn = bool(args.sync_bn) and world > 1
+    if sync_bn:  # main_vpo_mono.py:130: the reference's multi-GPU launch converts every BatchNorm
+        model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
     if world > 1:  # identical initial weights on every rank (DDP broadcasts rank 0's)
         for t in list(model.parameters()) + list(model.buffers()):
             dist.broadcast(t.data, 0)
@@ -560,7 +563,9 @@ def run_ours(args):
                                             "dgrad GEMMs, TF32 weight gradients, fp32 activations / BN statistics / "
                                             "LayerNorm / losses; stems and classifier fp32-grade"}[args.prec],
                            "l2": "working set per step (>10 GB of activations) far exceeds the 126 MB L2; no flush needed",
-                           "bn": "local (per-rank) BatchNorm statistics",
+                           "bn": ("SyncBatchNorm: fp64 [sum, sum^2, count] of every BN layer all-reduced on the device in "
+                                  "forward and backward (--sync-bn)") if sync_bn
+                           else "local (per-rank) BatchNorm statistics",
                            "allreduce": (f"5 gradient buckets produced in place, NCCL all-reduce(AVG) of each bucket launched "
                                          f"asynchronously from a backward-tape marker (overlaps the rest of the backward); "
                                          f"NCCL max_ctas={os.environ.get('CAVP_NCCL_MAX_CTAS', NCCL_MAX_CTAS_DEFAULT)}")
@@ -596,6 +601,9 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=None,
                     help="images per CPU reference step (default: 32 for --impl reference, 8 for the inline cpu_baseline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sync-bn", action="store_true",
+                    help="N > 1: convert the BatchNorms to SyncBatchNorm as the reference's multi-GPU launch does "
+                         "(main_vpo_mono.py:130); default: per-rank statistics")
     ap.add_argument("--mem-trace", action="store_true", help="print live / peak / reserved device memory after each set-up step")
     ap.add_argument("--no-stock-baseline", action="store_true",
                     help="skip the stock-PyTorch-on-this-GPU arm (gpu_stock_baseline) and the TF32 peak measurement")
