@@ -354,6 +354,17 @@ class Graph:
                 cache.refresh_transposed(self)  # the dgrad operands of every layer, one launch
         self.wcache = cache
 
+    def all_reduce_stats(self, t):
+        """In-place sum of a small SyncBatchNorm statistics vector over `sync_bn_group`: one peer-memory kernel
+        (csrc/peer.cu) when the ranks of the group can map each other's memory, else torch.distributed (NCCL)."""
+        from .parallel import peer_reduce_for
+        red = peer_reduce_for(self.sync_bn_group, self.device)
+        if red is not None and t.numel() * t.element_size() <= red.SLOT_BYTES:
+            self.call("cavp_peer_allreduce", *red.args(t))
+        else:
+            import torch.distributed as dist
+            dist.all_reduce(t, group=self.sync_bn_group)
+
     # ------------------------------------------------------------------ small helpers
     def call(self, name, *args):
         self.launches += 1
@@ -756,7 +767,7 @@ class Graph:
             import torch.distributed as dist
             sums = self.empty(2 * C + 1, dtype=torch.float64)
             self.call("cavp_bn_finalize", *head, count, *tail, sums.data_ptr(), 1, 0)
-            dist.all_reduce(sums, group=self.sync_bn_group)
+            self.all_reduce_stats(sums)
             self.call("cavp_bn_finalize", *head, count, *tail, sums.data_ptr(), 2, nbt)
             count_dev = sums.data_ptr() + 8 * 2 * C
             sync_sums = sums
@@ -786,7 +797,7 @@ class Graph:
             if sync:
                 import torch.distributed as dist
                 local = sums.clone()
-                dist.all_reduce(sums, group=self.sync_bn_group)
+                self.all_reduce_stats(sums)
             self.add_param_grad(bn.bias, local[0])
             self.add_param_grad(bn.weight, local[1])
             dy, acc_y = self.grad_target(y)

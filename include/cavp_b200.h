@@ -265,6 +265,19 @@ int cavp_avc_loss(const float* partials, int nchunk, int b, int c, const float* 
 int cavp_avc_bwd(const float* fv, const unsigned char* mask, const float* dms, const float* dnn, const float* gscale,
                  int b, int hw, int c, float* dfv, void* stream);
 
+/* ---- SyncBatchNorm statistics over NVLink peer memory (csrc/peer.cu) --------------------------------
+ * Replace the two small NCCL collectives torch.nn.SyncBatchNorm issues per layer and step (main_vpo_mono.py:130).
+ * Every rank allocates one exchange buffer (cavp_peer_alloc: cudaMalloc + CUDA IPC handle, 64 bytes), opens the buffers
+ * of the other ranks of the node (cavp_peer_open) and then calls cavp_peer_allreduce with the same, increasing `seq`
+ * (1, 2, ...) on every rank: io[0..n) (double if is_f64 else float) becomes the sum over ranks, added in rank order
+ * (bit-identical on every rank).  bases[r] = rank r's buffer as mapped in THIS process; n * sizeof(element) <=
+ * slot_bytes; world <= 8.  A peer that never arrives turns the result into NaN after ~30 s instead of hanging. */
+int cavp_peer_alloc(long long slot_bytes, void** buf, unsigned char* handle64);
+int cavp_peer_open(const unsigned char* handle64, void** buf);
+int cavp_peer_close(void* buf, int own);
+int cavp_peer_allreduce(void* io, int n, int is_f64, void* const* bases, int rank, int world, long long slot_bytes,
+                        int seq, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,9 +11,11 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu2
 
 
+@pytest.mark.parametrize("peer", ["0", "1"], ids=["nccl", "peer_memory"])
 @pytest.mark.skipif(int(os.environ.get("WORLD_SIZE", "1")) != 2 or not torch.cuda.is_available(),
                     reason="needs torchrun with 2 GPUs")
-def test_syncbn_conv_bn_matches_full_batch():
+def test_syncbn_conv_bn_matches_full_batch(peer, monkeypatch):
+    monkeypatch.setenv("CAVP_SYNCBN_PEER", peer)  # statistics over NCCL / over the peer-memory kernel (csrc/peer.cu)
     import torch.distributed as dist
     from cavp_b200.engine import Graph, new_act
     rank = int(os.environ["RANK"])
@@ -58,3 +60,37 @@ def test_syncbn_conv_bn_matches_full_batch():
     gg = g.param_grads[id(sbn.weight)].double().clone()
     dist.all_reduce(gg)
     assert float((gg.cpu() - bnd.weight.grad).abs().max() / bnd.weight.grad.abs().max()) < 2e-5
+
+
+@pytest.mark.skipif(int(os.environ.get("WORLD_SIZE", "1")) != 2 or not torch.cuda.is_available(),
+                    reason="needs torchrun with 2 GPUs")
+def test_peer_memory_allreduce_matches_nccl_bit_for_bit(monkeypatch):
+    """csrc/peer.cu: the single-kernel all-reduce over CUDA-IPC peer memory that carries the SyncBatchNorm statistics.
+    With two ranks a + b has one rounding, so it must equal NCCL's sum bit for bit - for fp64 [2C+1] and fp32 [2C]
+    vectors of every BatchNorm width of the model, back to back (the double-buffered slots and the sequence flags)."""
+    import torch.distributed as dist
+    from cavp_b200.parallel import peer_reduce_for
+    rank = int(os.environ["RANK"])
+    torch.cuda.set_device(rank)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+    dev = torch.device("cuda", rank)
+    monkeypatch.setenv("CAVP_SYNCBN_PEER", "1")  # opt-in path
+    red = peer_reduce_for(dist.group.WORLD, dev)
+    assert red is not None, "two GPUs of one node must be able to map each other's memory"
+    gen = torch.Generator(device=dev).manual_seed(100 + rank)
+    pairs = []
+    for it in range(300):
+        C = (1, 3, 64, 256, 304, 1024, 2048, 4095)[it % 8]
+        dt, n = ((torch.float64, 2 * C + 1) if it % 3 else (torch.float32, 2 * C))
+        x = torch.randn(n, device=dev, dtype=dt, generator=gen)
+        want = x.clone()
+        dist.all_reduce(want)
+        pairs.append((red.all_reduce_(x), want))
+        if it % 50 == 7:  # let one rank run ahead / fall behind
+            torch.cuda.synchronize()
+            if rank == it % 2:
+                torch.cuda._sleep(20_000_000)
+    torch.cuda.synchronize()
+    for got, want in pairs:
+        assert torch.equal(got, want)
