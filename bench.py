@@ -90,25 +90,68 @@ def make_args(B, device, prec):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe): ONE `nvidia-smi -lms`
+    process started before the region and killed after it; only the lines that arrive while the region is armed are
+    kept.  (A fresh nvidia-smi per sample re-initialises NVML every time, which stalls this process' kernel launches
+    for tens of ms - visible as a GPU bubble in the first timed step, when the host has no lead over the device.)
+    If the looping process produces no line within 3 s the sampler falls back to one nvidia-smi per sample."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    PERIOD_MS = 100
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag = index, [], False
+        self.armed, self.proc, self.first_line, self.oneshot = False, None, threading.Event(), False
+
+    def _cmd(self, loop):
+        return (["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)]
+                + (["-lms", str(self.PERIOD_MS)] if loop else []))
 
     def run(self):
+        try:
+            self.proc = subprocess.Popen(self._cmd(True), stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+                                         bufsize=1)
+            for line in self.proc.stdout:
+                self.first_line.set()
+                if self.armed and line.strip():
+                    self.samples.append([x.strip() for x in line.split(",")])
+                if self.stop_flag or self.oneshot:
+                    break
+        except Exception:
+            pass
+
+    def _oneshot_loop(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
+                out = subprocess.run(self._cmd(False), capture_output=True, text=True, timeout=5).stdout.strip()
+                if out and self.armed:
                     self.samples.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
             time.sleep(0.2)
+
+    def arm(self):
+        """Call right before the timed region: waits until the looping nvidia-smi is up, then starts keeping samples."""
+        if not self.first_line.wait(timeout=3.0):
+            self.oneshot = True
+            if self.proc is not None:
+                try:
+                    self.proc.kill()
+                except Exception:
+                    pass
+            threading.Thread(target=self._oneshot_loop, daemon=True).start()
+        self.armed = True
+
+    def stop(self):
+        self.stop_flag = True
+        self.armed = False
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
 
     def summary(self):
         sm = [float(s[1]) for s in self.samples if len(s) > 2 and s[1].replace(".", "").isdigit()]
@@ -432,22 +475,52 @@ def run_ours(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         sampler = ClockSampler(local_rank)
         sampler.start()
+        sampler.arm()
         e0.record()
         t_host = time.perf_counter()
+        marks = []
+        if args.trace_steps:
+            import gc
+            gc_log, gc_t0 = [], [0.0]
+
+            def on_gc(phase, info):
+                if phase == "start":
+                    gc_t0[0] = time.perf_counter()
+                else:
+                    gc_log.append((info["generation"], round(1e3 * (time.perf_counter() - gc_t0[0]), 2),
+                                   info["collected"], len(marks)))
+            gc.callbacks.append(on_gc)
         for _ in range(args.steps):
             step(resident)
+            if args.trace_steps:  # per-step device time and host time (diagnostic; adds one event record per step)
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                marks.append((ev, time.perf_counter()))
         if not resident:
             drain_readback()  # the last step's losses, still inside the timed region
         host_ms[0] = 1e3 * (time.perf_counter() - t_host) / args.steps  # time to ISSUE a step (no device sync)
         e1.record()
         torch.cuda.synchronize()
-        sampler.stop_flag = True
+        sampler.stop()
         if world > 1:
             dist.barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         sampler.join(timeout=2)
+        if args.trace_steps:
+            gc.callbacks.remove(on_gc)
+            slow = [x for x in gc_log if x[1] > 1.0]
+            print(f"[trace] python gc: {len(gc_log)} collections, (generation, ms, collected, during step) of those over "
+                  f"1 ms: {slow}", file=sys.stderr, flush=True)
+        if marks and rank == 0:
+            prev_e, prev_t, dev_ms, issue_ms = e0, t_host, [], []
+            for ev, t in marks:
+                dev_ms.append(round(prev_e.elapsed_time(ev), 2))
+                issue_ms.append(round(1e3 * (t - prev_t), 2))
+                prev_e, prev_t = ev, t
+            print(f"[trace] {'resident' if resident else 'e2e'} loop: device ms per step {dev_ms}; host ms to issue "
+                  f"each step {issue_ms}", file=sys.stderr, flush=True)
         return float(ms) / args.steps, sampler.summary(), launches[0] // args.steps
 
     # allocator priming (part of set-up, like building the model): the first steps of a process still grow the caching
@@ -604,6 +677,7 @@ def main():
     ap.add_argument("--sync-bn", action="store_true",
                     help="N > 1: convert the BatchNorms to SyncBatchNorm as the reference's multi-GPU launch does "
                          "(main_vpo_mono.py:130); default: per-rank statistics")
+    ap.add_argument("--trace-steps", action="store_true", help="print device and host time of every timed step")
     ap.add_argument("--mem-trace", action="store_true", help="print live / peak / reserved device memory after each set-up step")
     ap.add_argument("--no-stock-baseline", action="store_true",
                     help="skip the stock-PyTorch-on-this-GPU arm (gpu_stock_baseline) and the TF32 peak measurement")
