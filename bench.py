@@ -683,6 +683,8 @@ def main():
                     help="skip the stock-PyTorch-on-this-GPU arm (gpu_stock_baseline) and the TF32 peak measurement")
     ap.add_argument("--dump-profile", default=None, help="write the per-launch CUDA-event profile of one step here")
     args = ap.parse_args()
+    if args.cpu_batch is not None and args.cpu_batch < 2:
+        ap.error("--cpu-batch must be >= 2 (train-mode BatchNorm of the pooled ASPP branch needs two images, as in the reference)")
     select_config(args.config if args.config is not None else (2 if args.prec == 3 else 1))
     if args.impl == "reference":
         run_reference(args)
